@@ -1,0 +1,737 @@
+// Stage 1: hooked feature maps -> patch embeddings Z (fp32) + tensor-core operands (hi/lo).
+//
+// Replaces AnomalyClusteringCore._embed after the backbone
+// (reference: Anomaly-Clustering/models/patchcore/patchcore.py:368-431, common.py:145-183).
+//
+// Closed form implemented here:
+//   Z[b, y, x, t] = (1/|G_t|) sum_{g in G_t} (1/|F_g|) sum_{f in F_g} U_l(g)[b, f, y, x]
+//   G_t = adaptive-pool window of t over the L*Dp concat (Aggregator),
+//   F_g = adaptive-pool window of d = g % Dp over the C*k*k flat patch vector (MeanMapper),
+//   U_l[b, f=(c,ki,kj), y', x'] = LN_l(b)[c, y'*s - pad + ki, x'*s - pad + kj] (0 outside the map),
+//   layers whose patch grid differs from layer 0 are resampled plane-wise (bilinear,
+//   align_corners=False) AFTER the unfold, as the reference does.
+// Everything after the LayerNorm is a fixed sparse linear map, so one CTA stages the (LayerNorm'd,
+// zero-padded) input rows it needs in shared memory once and every thread evaluates "its" output
+// columns t for all positions of the row with per-thread tap tables held in registers.  HBM sees
+// each feature map once and each Z element once; no im2col tensor exists.
+#include "common.cuh"
+#include <vector>
+#include <algorithm>
+#include <cstring>
+
+namespace ac {
+
+static constexpr int kMaxLayers = 8;
+static constexpr int kThreads = 256;
+static constexpr int kTPT = 2;            // output columns per thread
+static constexpr int kStatSplit = 32;     // partial-sum blocks per (image, layer)
+
+struct LayerDev {
+  const float* ptr;
+  int C, H, W;
+  long long sb, sc, sh, sw;
+  int gh, gw;     // unfold grid of this layer
+  int CK;         // C*k*k
+  int resample;   // grid differs from layer 0
+};
+
+struct ChunkDesc {
+  int layer;
+  int t0, t1;     // output columns [t0, t1)
+  int c_lo, nch;  // staged channel range
+  int maxtaps;
+};
+
+struct EmbedParams {
+  LayerDev layers[kMaxLayers];
+  int L, B, k, s, pad, Dp;
+  int agg_in, agg_out;   // Aggregator pool: agg_in = L*Dp -> agg_out (== D when fused, else L*Dp)
+  int h0, w0;
+  int xseg_len, nxseg;
+  int layernorm;
+  float eps;
+  float* Z;              // [B*P0, ldz] or null
+  void* Zhi;
+  void* Zlo;
+  int op_dtype;
+  long long ldz;
+  const double* stats;   // [B][L][kStatSplit][2]
+};
+
+struct LaunchGeom {
+  int chan_contig;       // smem tile is [row][col][chan] (token layout) else [chan][row][col]
+  int SC, SR, SX;        // smem strides (elements)
+  int nrows_max, ncols_max;
+};
+
+// ------------------------------------------------------------------------------------------------
+// tap enumeration (host + device): output column t -> list of (f, weight) on layer `layer`
+template <typename F>
+__host__ __device__ inline void for_each_tap(int t, int agg_in, int agg_out, int Dp, int CK, F&& fn) {
+  const int g0 = pool_start(t, agg_in, agg_out), g1 = pool_end(t, agg_in, agg_out);
+  const float wg = 1.0f / (float)(g1 - g0);
+  for (int g = g0; g < g1; ++g) {
+    const int d = g % Dp;
+    const int f0 = pool_start(d, CK, Dp), f1 = pool_end(d, CK, Dp);
+    const float w = wg / (float)(f1 - f0);
+    for (int f = f0; f < f1; ++f) fn(f, w);
+  }
+}
+
+__host__ __device__ inline int tap_offset(int f, int k, int c_lo, int SC, int SR, int SX) {
+  const int kk = k * k;
+  const int c = f / kk, rem = f - c * kk;
+  const int ki = rem / k, kj = rem - ki * k;
+  return (c - c_lo) * SC + ki * SR + kj * SX;
+}
+
+// PyTorch upsample_bilinear2d source index, align_corners=False
+__host__ __device__ inline void bilinear_src(int dst, int in_size, int out_size, int& i0, int& i1, float& l1) {
+  const float scale = (float)in_size / (float)out_size;
+#ifdef __CUDA_ARCH__
+  float src = __fsub_rn(__fmul_rn(scale, (float)dst + 0.5f), 0.5f);  // no FMA contraction: same rounding as the host plan
+#else
+  volatile float prod = scale * ((float)dst + 0.5f);
+  float src = prod - 0.5f;
+#endif
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-(image, layer) sum / sum of squares partials for the whole-map LayerNorm (patchcore.py:384)
+__global__ void __launch_bounds__(256) ln_stats_kernel(EmbedParams p, double* stats) {
+  const int l = blockIdx.y, b = blockIdx.z;
+  const LayerDev ly = p.layers[l];
+  const long long n = (long long)ly.C * ly.H * ly.W;
+  const float* base = ly.ptr + (long long)b * ly.sb;
+  // dense images (any axis permutation) can be walked flat
+  long long lo_e = n * blockIdx.x / gridDim.x, hi_e = n * (blockIdx.x + 1) / gridDim.x;
+  float s = 0.f, q = 0.f;
+  const bool tok = (ly.sc == 1 && ly.sw == ly.C && ly.sh == (long long)ly.W * ly.C);
+  const bool cnn = (ly.sw == 1 && ly.sh == ly.W && ly.sc == (long long)ly.H * ly.W);
+  if (tok || cnn) {
+    for (long long e = lo_e + threadIdx.x; e < hi_e; e += blockDim.x) {
+      const float v = __ldg(base + e);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+  } else {
+    const int HW = ly.H * ly.W;
+    for (long long e = lo_e + threadIdx.x; e < hi_e; e += blockDim.x) {
+      const int c = (int)(e / HW);
+      const int r = (int)(e - (long long)c * HW);
+      const int y = r / ly.W, x = r - y * ly.W;
+      const float v = __ldg(base + c * ly.sc + y * ly.sh + x * ly.sw);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+  }
+  __shared__ double sh_s[8], sh_q[8];
+  double ds = warp_sum((double)s), dq = warp_sum((double)q);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sh_s[w] = ds; sh_q[w] = dq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c2 = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh_s[i]; c2 += sh_q[i]; }
+    double* o = stats + (((long long)b * p.L + l) * kStatSplit + blockIdx.x) * 2;
+    o[0] = a;
+    o[1] = c2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T to_op(float v);
+template <> __device__ __forceinline__ __half to_op<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 to_op<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float op_to_float(__half v) { return __half2float(v); }
+__device__ __forceinline__ float op_to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ void store_out(const EmbedParams& p, long long row, int t, float v) {
+  const long long idx = row * p.ldz + t;
+  if (p.Z) p.Z[idx] = v;
+  if (p.Zhi) {
+    if (p.op_dtype == AC_DT_F16) {
+      const __half h = __float2half_rn(v);
+      reinterpret_cast<__half*>(p.Zhi)[idx] = h;
+      if (p.Zlo) reinterpret_cast<__half*>(p.Zlo)[idx] = __float2half_rn(v - __half2float(h));
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      reinterpret_cast<__nv_bfloat16*>(p.Zhi)[idx] = h;
+      if (p.Zlo) reinterpret_cast<__nv_bfloat16*>(p.Zlo)[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// MAXTAPS > 0: per-thread tap tables in registers.  MAXTAPS == 0: taps re-enumerated on the fly
+// (any pooling ratio / patch size; slow path).
+template <int MAXTAPS, bool RESAMPLE>
+__global__ void __launch_bounds__(kThreads) embed_kernel(EmbedParams p, const ChunkDesc* __restrict__ chunks,
+                                                         int chunk_base, LaunchGeom g) {
+  extern __shared__ float tile[];
+  __shared__ float s_mu, s_rstd;
+  __shared__ int s_xo0[RESAMPLE ? 256 : 1], s_xo1[RESAMPLE ? 256 : 1];
+  __shared__ float s_lx[RESAMPLE ? 256 : 1];
+
+  const ChunkDesc ck = chunks[chunk_base + blockIdx.x];
+  const LayerDev ly = p.layers[ck.layer];
+  const int y = blockIdx.y / p.nxseg, xseg = blockIdx.y - y * p.nxseg;
+  const int b = blockIdx.z;
+  const int xa = xseg * p.xseg_len, xb = min(p.w0, xa + p.xseg_len);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- LayerNorm statistics of (image b, layer) from the pre-pass partials
+  if (warp == 0) {
+    float mu = 0.f, rstd = 1.f;
+    if (p.layernorm) {
+      const double* st = p.stats + (((long long)b * p.L + ck.layer) * kStatSplit) * 2;
+      double a = 0, q = 0;
+      for (int i = lane; i < kStatSplit; i += 32) { a += st[2 * i]; q += st[2 * i + 1]; }
+      a = warp_sum(a);
+      q = warp_sum(q);
+      const double n = (double)ly.C * ly.H * ly.W;
+      const double m = a / n;
+      double var = q / n - m * m;
+      if (var < 0) var = 0;
+      mu = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+    if (lane == 0) { s_mu = mu; s_rstd = rstd; }
+  }
+
+  // ---- tile geometry (input rows / cols staged for this output row segment)
+  int in_row0, nrows, in_col0, ncols, dyrow = 0;
+  float wy1 = 0.f;
+  if (!RESAMPLE) {
+    in_row0 = y * p.s - p.pad;
+    nrows = p.k;
+    in_col0 = xa * p.s - p.pad;
+    ncols = (xb - xa - 1) * p.s + p.k;
+  } else {
+    int y0, y1;
+    bilinear_src(y, ly.gh, p.h0, y0, y1, wy1);
+    in_row0 = y0 * p.s - p.pad;
+    dyrow = (y1 - y0) * p.s;
+    nrows = dyrow + p.k;
+    int xl0, xl1, xh0, xh1;
+    float tmp;
+    bilinear_src(xa, ly.gw, p.w0, xl0, xl1, tmp);
+    bilinear_src(xb - 1, ly.gw, p.w0, xh0, xh1, tmp);
+    in_col0 = xl0 * p.s - p.pad;
+    ncols = (xh1 - xl0) * p.s + p.k;
+    for (int x = xa + tid; x < xb; x += kThreads) {
+      int x0, x1;
+      float l1;
+      bilinear_src(x, ly.gw, p.w0, x0, x1, l1);
+      s_xo0[x - xa] = (x0 - xl0) * p.s * g.SX;
+      s_xo1[x - xa] = (x1 - xl0) * p.s * g.SX;
+      s_lx[x - xa] = l1;
+    }
+  }
+  __syncthreads();
+  const float mu = s_mu, rstd = s_rstd;
+
+  // ---- stage: (v - mu) * rstd inside the map, literal zeros outside (the reference pads AFTER LN)
+  const float* src = ly.ptr + (long long)b * ly.sb + (long long)ck.c_lo * ly.sc;
+  if (g.chan_contig) {
+    const int npos = nrows * ncols;
+    for (int pos = warp; pos < npos; pos += kThreads / 32) {
+      const int r = pos / ncols, xx = pos - r * ncols;
+      const int iy = in_row0 + r, ix = in_col0 + xx;
+      const bool inside = (iy >= 0) && (iy < ly.H) && (ix >= 0) && (ix < ly.W);
+      float* dst = tile + r * g.SR + xx * g.SX;
+      const float* s0 = src + (long long)iy * ly.sh + (long long)ix * ly.sw;
+      for (int c = lane; c < ck.nch; c += 32) dst[c] = inside ? (__ldg(s0 + c) - mu) * rstd : 0.f;
+    }
+  } else {
+    const int ncr = ck.nch * nrows;
+    for (int cr = warp; cr < ncr; cr += kThreads / 32) {
+      const int c = cr / nrows, r = cr - c * nrows;
+      const int iy = in_row0 + r;
+      const bool rin = (iy >= 0) && (iy < ly.H);
+      float* dst = tile + c * g.SC + r * g.SR;
+      const float* s0 = src + (long long)c * ly.sc + (long long)iy * ly.sh;
+      for (int xx = lane; xx < ncols; xx += 32) {
+        const int ix = in_col0 + xx;
+        const bool inside = rin && (ix >= 0) && (ix < ly.W);
+        dst[xx * g.SX] = inside ? (__ldg(s0 + (long long)ix * ly.sw) - mu) * rstd : 0.f;
+      }
+    }
+  }
+
+  // ---- per-thread tap tables
+  int tcol[kTPT];
+  bool tvalid[kTPT];
+  int off[kTPT][MAXTAPS > 0 ? MAXTAPS : 1];
+  float wt[kTPT][MAXTAPS > 0 ? MAXTAPS : 1];
+  int ntap[kTPT];
+#pragma unroll
+  for (int j = 0; j < kTPT; ++j) {
+    tcol[j] = ck.t0 + tid + j * kThreads;
+    tvalid[j] = tcol[j] < ck.t1;
+    ntap[j] = 0;
+    if (MAXTAPS > 0) {
+#pragma unroll
+      for (int q = 0; q < MAXTAPS; ++q) { off[j][q] = 0; wt[j][q] = 0.f; }
+      if (tvalid[j]) {
+        int n = 0;
+        for_each_tap(tcol[j], p.agg_in, p.agg_out, p.Dp, ly.CK, [&](int f, float w) {
+          const int o = tap_offset(f, p.k, ck.c_lo, g.SC, g.SR, g.SX);
+#pragma unroll
+          for (int q = 0; q < MAXTAPS; ++q)
+            if (q == n) { off[j][q] = o; wt[j][q] = w; }
+          ++n;
+        });
+        ntap[j] = n;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- evaluate every position of the row segment
+  const long long row0 = ((long long)b * p.h0 + y) * p.w0;
+#pragma unroll 2
+  for (int x = xa; x < xb; ++x) {
+    float acc[kTPT];
+    if (!RESAMPLE) {
+      const float* tb = tile + (x - xa) * p.s * g.SX;
+#pragma unroll
+      for (int j = 0; j < kTPT; ++j) {
+        float a = 0.f;
+        if (MAXTAPS > 0) {
+#pragma unroll
+          for (int q = 0; q < MAXTAPS; ++q) {
+            const float v = tb[off[j][q]];
+            a = (q < ntap[j]) ? fmaf(wt[j][q], v, a) : a;  // unused slots never touch the sum (NaN-safe)
+          }
+        } else if (tvalid[j]) {
+          for_each_tap(tcol[j], p.agg_in, p.agg_out, p.Dp, ly.CK, [&](int f, float w) {
+            a = fmaf(w, tb[tap_offset(f, p.k, ck.c_lo, g.SC, g.SR, g.SX)], a);
+          });
+        }
+        acc[j] = a;
+      }
+    } else {
+      const float lx1 = s_lx[x - xa], lx0 = 1.f - lx1, ly0 = 1.f - wy1;
+      const float* t00 = tile + s_xo0[x - xa];
+      const float* t01 = tile + s_xo1[x - xa];
+      const float* t10 = t00 + dyrow * g.SR;
+      const float* t11 = t01 + dyrow * g.SR;
+#pragma unroll
+      for (int j = 0; j < kTPT; ++j) {
+        float a = 0.f;
+        auto tap = [&](int o, float w, bool on) {
+          const float v = ly0 * (lx0 * t00[o] + lx1 * t01[o]) + wy1 * (lx0 * t10[o] + lx1 * t11[o]);
+          a = on ? fmaf(w, v, a) : a;
+        };
+        if (MAXTAPS > 0) {
+#pragma unroll
+          for (int q = 0; q < MAXTAPS; ++q) tap(off[j][q], wt[j][q], q < ntap[j]);
+        } else if (tvalid[j]) {
+          for_each_tap(tcol[j], p.agg_in, p.agg_out, p.Dp, ly.CK, [&](int f, float w) {
+            tap(tap_offset(f, p.k, ck.c_lo, g.SC, g.SR, g.SX), w, true);
+          });
+        }
+        acc[j] = a;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kTPT; ++j)
+      if (tvalid[j]) store_out(p, row0 + x, tcol[j], acc[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone compat kernels
+__global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int H, int W, int k, int s, int pad,
+                                int gh, int gw, float* __restrict__ out) {
+  // out [B, gh*gw, C, k, k]
+  const long long total = (long long)B * gh * gw * C * k * k;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long r = e;
+    const int kj = (int)(r % k); r /= k;
+    const int ki = (int)(r % k); r /= k;
+    const int c = (int)(r % C); r /= C;
+    const int px = (int)(r % gw); r /= gw;
+    const int py = (int)(r % gh); r /= gh;
+    const int b = (int)r;
+    const int iy = py * s - pad + ki, ix = px * s - pad + kj;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((long long)b * C + c) * H + iy) * W + ix);
+    out[e] = v;
+  }
+}
+
+__global__ void pool1d_kernel(const float* __restrict__ in, long long rows, int Lin, int Lout, float* __restrict__ out) {
+  const long long total = rows * Lout;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / Lout;
+    const int d = (int)(e - r * Lout);
+    const int f0 = pool_start(d, Lin, Lout), f1 = pool_end(d, Lin, Lout);
+    const float* src = in + r * Lin;
+    float a = 0.f;
+    for (int f = f0; f < f1; ++f) a += __ldg(src + f);
+    out[e] = a / (float)(f1 - f0);
+  }
+}
+
+template <typename T>
+__global__ void split_kernel(const float* __restrict__ x, long long n, T* __restrict__ hi, T* __restrict__ lo) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float v = x[e];
+    const T h = to_op<T>(v);
+    hi[e] = h;
+    if (lo) lo[e] = to_op<T>(v - op_to_float(h));
+  }
+}
+
+__device__ __forceinline__ float ld_as_float(const float* p, long long i) { return __ldg(p + i); }
+__device__ __forceinline__ float ld_as_float(const __half* p, long long i) { return __half2float(p[i]); }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+
+// one warp per row
+template <typename T>
+__global__ void __launch_bounds__(256) row_norms_kernel(const T* __restrict__ A, const T* __restrict__ A2, long long rows, int D,
+                                                        float* __restrict__ n2) {
+  const long long r = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float v = ld_as_float(A, r * D + d);
+    if (A2) v += ld_as_float(A2, r * D + d);
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) n2[r] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host plan
+struct Plan {
+  EmbedParams p;
+  std::vector<ChunkDesc> chunks;
+  struct PerLayer { int chunk_base, nchunks, maxtaps, nch_max; LaunchGeom g; size_t smem; } pl[kMaxLayers];
+  bool fused;
+};
+
+static int conflict_score(const EmbedParams& p, const ChunkDesc& ck, const LayerDev& ly, int SC, int SR, int SX) {
+  // sum over (warp, tap slot) of the worst bank multiplicity for the first column of each thread
+  int score = 0;
+  std::vector<int> offs;
+  for (int w = 0; w < kThreads / 32; ++w) {
+    std::vector<std::vector<int>> per_lane(32);
+    size_t mx = 0;
+    for (int l = 0; l < 32; ++l) {
+      const int t = ck.t0 + w * 32 + l;
+      if (t >= ck.t1) continue;
+      for_each_tap(t, p.agg_in, p.agg_out, p.Dp, ly.CK,
+                   [&](int f, float) { per_lane[l].push_back(tap_offset(f, p.k, ck.c_lo, SC, SR, SX)); });
+      mx = std::max(mx, per_lane[l].size());
+    }
+    for (size_t q = 0; q < mx; ++q) {
+      int cnt[32] = {0};
+      // distinct addresses in the same bank conflict; identical addresses broadcast
+      std::vector<int> seen;
+      for (int l = 0; l < 32; ++l)
+        if (q < per_lane[l].size()) {
+          const int a = per_lane[l][q];
+          if (std::find(seen.begin(), seen.end(), a) == seen.end()) { seen.push_back(a); cnt[((a % 32) + 32) % 32]++; }
+        }
+      score += *std::max_element(cnt, cnt + 32);
+    }
+  }
+  return score;
+}
+
+static int build_plan(const ac_layer_t* layers, int L, int B, int k, int s, int Dp, int D, int layernorm, float eps,
+                      Plan& plan) {
+  if (L < 1 || L > kMaxLayers || B < 1 || k < 1 || s < 1 || Dp < 1 || D < 1) return AC_ERR_INVALID;
+  EmbedParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  p.L = L; p.B = B; p.k = k; p.s = s; p.pad = (k - 1) / 2; p.Dp = Dp;
+  p.layernorm = layernorm; p.eps = eps;
+  for (int l = 0; l < L; ++l) {
+    const ac_layer_t& a = layers[l];
+    if (!a.ptr || a.C < 1 || a.H < 1 || a.W < 1) return AC_ERR_INVALID;
+    LayerDev& d = p.layers[l];
+    d.ptr = a.ptr; d.C = a.C; d.H = a.H; d.W = a.W;
+    d.sb = a.sb; d.sc = a.sc; d.sh = a.sh; d.sw = a.sw;
+    d.gh = (a.H + 2 * p.pad - (k - 1) - 1) / s + 1;
+    d.gw = (a.W + 2 * p.pad - (k - 1) - 1) / s + 1;
+    if (d.gh < 1 || d.gw < 1) return AC_ERR_INVALID;
+    d.CK = a.C * k * k;
+  }
+  p.h0 = p.layers[0].gh; p.w0 = p.layers[0].gw;
+  for (int l = 0; l < L; ++l) p.layers[l].resample = (p.layers[l].gh != p.h0 || p.layers[l].gw != p.w0);
+  p.agg_in = L * Dp;
+  // fused aggregator iff no Aggregator window straddles two layers
+  bool fused = true;
+  for (int t = 0; t < D && fused; ++t) {
+    const int g0 = pool_start(t, p.agg_in, D), g1 = pool_end(t, p.agg_in, D);
+    if (g0 / Dp != (g1 - 1) / Dp) fused = false;
+  }
+  plan.fused = fused;
+  p.agg_out = fused ? D : p.agg_in;
+  p.ldz = p.agg_out;
+
+  // ---- choose chunking so that the staged tile fits shared memory
+  const size_t kSoft = 72 * 1024, kHard = 200 * 1024;
+  int tchunk = kThreads * kTPT;
+  p.xseg_len = p.w0;
+  for (int l = 0; l < L; ++l)
+    if (p.layers[l].resample) p.xseg_len = std::min(p.xseg_len, 256);  // s_xo tables hold 256 positions
+  for (;;) {
+    plan.chunks.clear();
+    size_t worst = 0;
+    p.nxseg = ceil_div(p.w0, p.xseg_len);
+    for (int l = 0; l < L; ++l) {
+      const LayerDev& ly = p.layers[l];
+      Plan::PerLayer& pl = plan.pl[l];
+      pl.chunk_base = (int)plan.chunks.size();
+      pl.maxtaps = 0; pl.nch_max = 0;
+      // columns owned by this layer
+      int ta = -1, tb = -1;
+      for (int t = 0; t < p.agg_out; ++t) {
+        const int lay = pool_start(t, p.agg_in, p.agg_out) / Dp;
+        if (lay == l) { if (ta < 0) ta = t; tb = t + 1; }
+      }
+      if (ta < 0) { pl.nchunks = 0; continue; }
+      for (int t0 = ta; t0 < tb; t0 += tchunk) {
+        ChunkDesc ck;
+        ck.layer = l; ck.t0 = t0; ck.t1 = std::min(tb, t0 + tchunk);
+        int fmin = 1 << 30, fmax = -1, mt = 0;
+        for (int t = ck.t0; t < ck.t1; ++t) {
+          int n = 0;
+          for_each_tap(t, p.agg_in, p.agg_out, Dp, ly.CK, [&](int f, float) { fmin = std::min(fmin, f); fmax = std::max(fmax, f); ++n; });
+          mt = std::max(mt, n);
+        }
+        ck.c_lo = fmin / (k * k);
+        ck.nch = fmax / (k * k) - ck.c_lo + 1;
+        ck.maxtaps = mt;
+        pl.maxtaps = std::max(pl.maxtaps, mt);
+        pl.nch_max = std::max(pl.nch_max, ck.nch);
+        plan.chunks.push_back(ck);
+      }
+      pl.nchunks = (int)plan.chunks.size() - pl.chunk_base;
+      // tile extents
+      LaunchGeom& g = pl.g;
+      if (!ly.resample) {
+        g.nrows_max = k;
+        g.ncols_max = (std::min(p.xseg_len, p.w0) - 1) * s + k;
+      } else {
+        g.nrows_max = s + k;
+        // widest coarse span over all segments
+        int span = 1;
+        for (int xs = 0; xs < p.nxseg; ++xs) {
+          const int xa = xs * p.xseg_len, xb = std::min(p.w0, xa + p.xseg_len);
+          int a0, a1, b0, b1; float tmp;
+          bilinear_src(xa, ly.gw, p.w0, a0, a1, tmp);
+          bilinear_src(xb - 1, ly.gw, p.w0, b0, b1, tmp);
+          span = std::max(span, b1 - a0);
+        }
+        g.ncols_max = span * s + k;
+      }
+      g.chan_contig = (ly.sc == 1);
+      if (g.chan_contig) { g.SC = 1; g.SX = pl.nch_max; g.SR = g.ncols_max * g.SX; }
+      else { g.SX = 1; g.SR = g.ncols_max; g.SC = g.nrows_max * g.SR; }
+      pl.smem = (size_t)g.nrows_max * g.ncols_max * (pl.nch_max + 32) * sizeof(float);  // incl. padding headroom
+      worst = std::max(worst, pl.smem);
+    }
+    if (worst <= kSoft) break;
+    if (tchunk > 32) { tchunk /= 2; continue; }
+    if (worst <= kHard) break;
+    if (p.xseg_len > 1) { p.xseg_len = (p.xseg_len + 1) / 2; continue; }
+    return AC_ERR_UNSUPPORTED;
+  }
+  // ---- bank-conflict-aware padding of the channel / position pitch
+  for (int l = 0; l < L; ++l) {
+    Plan::PerLayer& pl = plan.pl[l];
+    if (pl.nchunks == 0) continue;
+    LaunchGeom& g = pl.g;
+    const ChunkDesc& ck = plan.chunks[pl.chunk_base];
+    int best = 1 << 30, best_pad = 0;
+    for (int padv = 0; padv < 32; ++padv) {
+      int SC, SR, SX;
+      if (g.chan_contig) { SC = 1; SX = pl.nch_max + padv; SR = g.ncols_max * SX; }
+      else { SX = 1; SR = g.ncols_max; SC = g.nrows_max * SR + padv; }
+      const int sc = conflict_score(p, ck, p.layers[l], SC, SR, SX);
+      if (sc < best) { best = sc; best_pad = padv; }
+    }
+    if (g.chan_contig) { g.SX = pl.nch_max + best_pad; g.SR = g.ncols_max * g.SX; pl.smem = (size_t)g.nrows_max * g.SR * sizeof(float); }
+    else { g.SC = g.nrows_max * g.SR + best_pad; pl.smem = (size_t)pl.nch_max * g.SC * sizeof(float); }
+  }
+  return AC_OK;
+}
+
+template <int MAXTAPS, bool RESAMPLE>
+static int launch_embed(const Plan& plan, int l, const ChunkDesc* dchunks, cudaStream_t st) {
+  const Plan::PerLayer& pl = plan.pl[l];
+  auto kern = embed_kernel<MAXTAPS, RESAMPLE>;
+  AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  dim3 grid(pl.nchunks, plan.p.h0 * plan.p.nxseg, plan.p.B);
+  kern<<<grid, kThreads, pl.smem, st>>>(plan.p, dchunks, pl.chunk_base, pl.g);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+template <bool RESAMPLE>
+static int dispatch_taps(const Plan& plan, int l, const ChunkDesc* dchunks, cudaStream_t st) {
+  const int mt = plan.pl[l].maxtaps;
+  if (mt <= 5) return launch_embed<5, RESAMPLE>(plan, l, dchunks, st);
+  if (mt <= 10) return launch_embed<10, RESAMPLE>(plan, l, dchunks, st);
+  if (mt <= 18) return launch_embed<18, RESAMPLE>(plan, l, dchunks, st);
+  if (mt <= 32) return launch_embed<32, RESAMPLE>(plan, l, dchunks, st);
+  return launch_embed<0, RESAMPLE>(plan, l, dchunks, st);
+}
+
+}  // namespace ac
+
+using namespace ac;
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static bool aggregator_fusable(int L, int Dp, int D) {
+  const int agg_in = L * Dp;
+  for (int t = 0; t < D; ++t) {
+    const int g0 = pool_start(t, agg_in, D), g1 = pool_end(t, agg_in, D);
+    if (g0 / Dp != (g1 - 1) / Dp) return false;
+  }
+  return true;
+}
+
+extern "C" size_t ac_embed_workspace_bytes(int L, int B, int64_t P, int Dp, int D) {
+  if (L < 1 || B < 1 || P < 1 || Dp < 1 || D < 1) return 0;
+  size_t stats = align256((size_t)B * L * kStatSplit * 2 * sizeof(double));
+  size_t chunks = align256(((size_t)L * Dp / 32 + (size_t)D / 32 + 2 * L + 16) * sizeof(ChunkDesc));
+  // the [B*P, L*Dp] concat scratch exists only when an Aggregator window straddles two layers
+  size_t concat = aggregator_fusable(L, Dp, D) ? 0 : align256((size_t)B * P * (size_t)L * Dp * sizeof(float));
+  return stats + chunks + concat;
+}
+
+extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, int stride, int Dp, int D, int layernorm,
+                        float eps, float* Z, void* Zhi, void* Zlo, int op_dtype, void* ws, size_t ws_bytes,
+                        ac_stream_t stream) {
+  if (!layers || !ws) return AC_ERR_INVALID;
+  if (!Z && !Zhi) return AC_ERR_INVALID;
+  if (Zhi && op_dtype != AC_DT_F16 && op_dtype != AC_DT_BF16) return AC_ERR_INVALID;
+  if (Zlo && !Zhi) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan plan;
+  rc = build_plan(layers, L, B, patchsize, stride, Dp, D, layernorm, eps, plan);
+  if (rc) return rc;
+  EmbedParams& p = plan.p;
+  const long long P0 = (long long)p.h0 * p.w0;
+
+  const size_t stats_b = align256((size_t)B * L * kStatSplit * 2 * sizeof(double));
+  const size_t chunks_b = align256(plan.chunks.size() * sizeof(ChunkDesc));
+  const size_t concat_b = plan.fused ? 0 : align256((size_t)B * P0 * p.agg_in * sizeof(float));
+  if (stats_b + chunks_b + concat_b > ws_bytes) return AC_ERR_WORKSPACE;
+  char* w8 = (char*)ws;
+  double* dstats = (double*)w8;
+  ChunkDesc* dchunks = (ChunkDesc*)(w8 + stats_b);
+  float* dconcat = (float*)(w8 + stats_b + chunks_b);
+  AC_CUDA(cudaMemcpyAsync(dchunks, plan.chunks.data(), plan.chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, st));
+
+  p.stats = dstats;
+  if (plan.fused) {
+    p.Z = Z; p.Zhi = Zhi; p.Zlo = Zlo; p.op_dtype = op_dtype;
+  } else {
+    p.Z = dconcat; p.Zhi = nullptr; p.Zlo = nullptr; p.op_dtype = 0;
+  }
+  if (layernorm) {
+    ln_stats_kernel<<<dim3(kStatSplit, L, B), 256, 0, st>>>(p, dstats);
+    AC_LAUNCH_CHECK();
+  }
+  for (int l = 0; l < L; ++l) {
+    if (plan.pl[l].nchunks == 0) continue;
+    rc = p.layers[l].resample ? dispatch_taps<true>(plan, l, dchunks, st) : dispatch_taps<false>(plan, l, dchunks, st);
+    if (rc) return rc;
+  }
+  if (!plan.fused) {
+    // Aggregator windows straddle layers: pool the concat [B*P, L*Dp] -> [B*P, D] in a second pass
+    const long long rows = (long long)B * P0;
+    float* zout = Z;
+    if (!zout) return AC_ERR_UNSUPPORTED;  // operand-only output needs the fused aggregator
+    const long long total = rows * D;
+    int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    pool1d_kernel<<<blocks, 256, 0, st>>>(dconcat, rows, p.agg_in, D, zout);
+    AC_LAUNCH_CHECK();
+    if (Zhi) {
+      rc = ac_split_operand(zout, total, Zhi, Zlo, op_dtype, stream);
+      if (rc) return rc;
+    }
+  }
+  return AC_OK;
+}
+
+extern "C" int ac_patchify(const float* x, int B, int C, int H, int W, int patchsize, int stride, float* out,
+                           int* grid_host, ac_stream_t stream) {
+  if (!x || !out || B < 1 || C < 1 || H < 1 || W < 1 || patchsize < 1 || stride < 1) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  const int pad = (patchsize - 1) / 2;
+  const int gh = (H + 2 * pad - (patchsize - 1) - 1) / stride + 1;
+  const int gw = (W + 2 * pad - (patchsize - 1) - 1) / stride + 1;
+  if (gh < 1 || gw < 1) return AC_ERR_INVALID;
+  if (grid_host) { grid_host[0] = gh; grid_host[1] = gw; }
+  const long long total = (long long)B * gh * gw * C * patchsize * patchsize;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+  patchify_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, B, C, H, W, patchsize, stride, pad, gh, gw, out);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+extern "C" int ac_adaptive_pool1d(const float* in, int64_t rows, int Lin, int Lout, float* out, ac_stream_t stream) {
+  if (!in || !out || rows < 0 || Lin < 1 || Lout < 1) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (rows == 0) return AC_OK;
+  const long long total = (long long)rows * Lout;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+  pool1d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, rows, Lin, Lout, out);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+extern "C" int ac_split_operand(const float* x, int64_t n, void* hi, void* lo, int dtype, ac_stream_t stream) {
+  if (!x || !hi || n < 0) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (n == 0) return AC_OK;
+  int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 32);
+  if (dtype == AC_DT_F16)
+    split_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, (__half*)hi, (__half*)lo);
+  else if (dtype == AC_DT_BF16)
+    split_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  else
+    return AC_ERR_INVALID;
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+extern "C" int ac_row_norms(const void* A, const void* A2, int dtype, int64_t rows, int D, float* n2, ac_stream_t stream) {
+  if (!A || !n2 || rows < 0 || D < 1) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (rows == 0) return AC_OK;
+  const int wpb = 8;
+  const unsigned blocks = (unsigned)((rows + wpb - 1) / wpb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == AC_DT_F32)
+    row_norms_kernel<float><<<blocks, 256, 0, st>>>((const float*)A, (const float*)A2, rows, D, n2);
+  else if (dtype == AC_DT_F16)
+    row_norms_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)A, (const __half*)A2, rows, D, n2);
+  else if (dtype == AC_DT_BF16)
+    row_norms_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)A2, rows, D, n2);
+  else
+    return AC_ERR_INVALID;
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}

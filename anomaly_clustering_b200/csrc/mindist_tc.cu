@@ -1,0 +1,512 @@
+// Stage 2: patch-versus-bank nearest neighbour on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// Replaces the torch.cdist + torch.min(dim=1) loops of Weight_Distance_Unsupervised / _Supervised
+// (reference: Anomaly-Clustering/models/patchcore/utils.py:222-237).
+//
+//   dmin[j, r] = sqrt(max(0, |q_r|^2 + min_{c in image j} (|b_c|^2 - 2 q_r . b_c)))
+//
+// Structure (one persistent CTA -- or CTA pair with cta_group::2 -- per SM):
+//   warp 0      TMA producer: 128B-swizzled K-major operand tiles -> kStages-deep smem ring
+//   warp 1      MMA issuer:   tcgen05.mma kind::f16, fp32 accumulators in TMEM (2 x 256 columns,
+//               double buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns, d2 = bn2[c] - 2*acc, running row-min in
+//               registers across the tiles of one bank image (each thread owns one query row, so
+//               the row-min needs no shuffles), sqrt + one coalesced store per (row, bank image).
+//   The [Mq, Nb*P] distance matrix never exists in memory.
+// Work unit = (block of 128*kCtaGroup query rows, bank image).  A bank image is cut into nt tiles
+// of <= 256 rows whose widths are multiples of 16 (P=784 -> 208+208+208+160), so no tile straddles
+// two images; excess columns of the last tile are masked with +inf norms.
+// Units are rasterised so that concurrently resident units share A blocks and bank images in L2.
+// The X3 precision modes run 3 K-segments (hi*hi, lo*hi, hi*lo) into the same accumulator.
+#include "common.cuh"
+#include <cuda.h>
+#include <algorithm>
+#include <cstring>
+
+namespace ac {
+
+static constexpr int kTcThreads = 192;
+static constexpr int kBlockK = 64;         // elements per K block = one 128-byte swizzle row (2-byte operands)
+static constexpr int kUmmaK = 16;
+static constexpr int kTileM = 128;         // rows per CTA
+static constexpr int kMaxN = 256;
+static constexpr int kTmemCols = 512;
+static constexpr long long kWatchdogCycles = 20000000000LL;  // ~10 s
+
+struct __align__(64) TcParams {
+  CUtensorMap mapA[2];       // [0] hi, [1] lo
+  CUtensorMap mapBmain[2];
+  CUtensorMap mapBlast[2];
+  const float* qn2;
+  const float* bn2;
+  float* dmin;
+  int* err;
+  long long Mq;
+  long long total_units;
+  int nb_img, P, D;
+  int nkb;                   // K blocks per segment
+  int nseg;                  // 1 or 3
+  int nt, wmain, wlast;      // tiles per bank image, widths (multiples of 16)
+  int n_mblocks, GM;
+  uint32_t idesc_main, idesc_last;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWatchdogCycles) {  // pipeline deadlock: report and kill the launch, never hang the GPU
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+template <int G>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  if (G == 1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+  } else {
+    // data lands in this CTA's shared memory, completion bytes are signalled on the LEADER CTA's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+
+template <int G>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  if (G == 1)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+template <int G>
+__device__ __forceinline__ void tmem_relinquish() {
+  if (G == 1)
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  else
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int G>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if (G == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int G>
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (G == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// tcgen05.commit: the mbarrier receives one arrival once all previously issued MMAs have completed
+template <int G>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (G == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else  // same barrier offset in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+#define AC_TMEM_LD16(taddr, v)                                                                                          \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),        \
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])   \
+               : "r"(taddr))
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row x 128-byte atoms, SBO = 1024 B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void decode_unit(const TcParams& p, long long u, int& mb, int& img) {
+  const long long per_group = (long long)p.GM * p.nb_img;
+  const int mg = (int)(u / per_group);
+  const long long rem = u - (long long)mg * per_group;
+  const int gm_cur = min(p.GM, p.n_mblocks - mg * p.GM);
+  img = (int)(rem / gm_cur);
+  mb = mg * p.GM + (int)(rem - (long long)img * gm_cur);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int G, int kStages>
+__global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int kBRows = kMaxN / G;                         // bank rows staged per CTA per stage
+  constexpr uint32_t kABytes = kTileM * kBlockK * 2;        // 16 KB
+  constexpr uint32_t kBBytes = kBRows * kBlockK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by SWIZZLE_128B; the launch adds 1 KB of slack
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* s_bn2 = reinterpret_cast<float*>(smem + kStages * kStageBytes);            // [2][kMaxN]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bn2 + 2 * kMaxN);
+  uint64_t* full_bar = s_bar;                 // [kStages]
+  uint64_t* empty_bar = s_bar + kStages;      // [kStages]
+  uint64_t* tfull_bar = s_bar + 2 * kStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (G == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  const long long worker = (G == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const long long nworkers = (G == 2) ? (gridDim.x >> 1) : gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull_bar[b]), 1);
+      mbar_init(smem_u32(&tempty_bar[b]), 4 * G);  // one arrival per epilogue warp of every CTA in the group
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<G>(smem_u32(s_tmem), kTmemCols);
+    tmem_relinquish<G>();
+  }
+  tc_fence_before();
+  if (G == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t full0 = (G == 2) ? mapa_rank(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
+      for (long long u = worker; u < p.total_units; u += nworkers) {
+        int mb, img;
+        decode_unit(p, u, mb, img);
+        const int arow = mb * (kTileM * G) + (int)rank * kTileM;
+        for (int t = 0; t < p.nt; ++t) {
+          const bool last = (t == p.nt - 1);
+          const int width = last ? p.wlast : p.wmain;
+          const int brow = img * p.P + t * p.wmain + (int)rank * (width / G);
+          const uint32_t bbytes = (uint32_t)(width / G) * kBlockK * 2;
+          for (int seg = 0; seg < p.nseg; ++seg) {
+            const CUtensorMap* ma = &p.mapA[seg == 1 ? 1 : 0];
+            const CUtensorMap* mbp = last ? &p.mapBlast[seg == 2 ? 1 : 0] : &p.mapBmain[seg == 2 ? 1 : 0];
+            for (int kb = 0; kb < p.nkb; ++kb) {
+              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.err, 1);
+              if (leader) mbar_expect_tx(smem_u32(&full_bar[stage]), (kABytes + bbytes) * G);
+              const uint32_t fb = full0 + stage * 8;
+              uint8_t* sa = smem + stage * kStageBytes;
+              tma_load_2d<G>(smem_u32(sa), ma, fb, kb * kBlockK, arow);
+              tma_load_2d<G>(smem_u32(sa + kABytes), mbp, fb, kb * kBlockK, brow);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA only)
+    if (leader && elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t tile_ctr = 0;
+      for (long long u = worker; u < p.total_units; u += nworkers) {
+        for (int t = 0; t < p.nt; ++t, ++tile_ctr) {
+          const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
+          const uint32_t idesc = (t == p.nt - 1) ? p.idesc_last : p.idesc_main;
+          mbar_wait(smem_u32(&tempty_bar[buf]), tphase ^ 1, p.err, 2);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kMaxN;
+          const int nk_total = p.nseg * p.nkb;
+          for (int kb = 0; kb < nk_total; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase, p.err, 3);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+            const uint64_t adesc = make_smem_desc(sa);
+            const uint64_t bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance 32 bytes (16 elements) along K inside the 128-byte swizzle row
+              umma_f16<G>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<G>(smem_u32(&empty_bar[stage]));     // frees the smem slot once these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit<G>(smem_u32(&tfull_bar[buf]));         // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 2..5)
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int et = q * 32 + lane;                 // row inside the CTA tile == TMEM lane
+    const int eidx = threadIdx.x - 64;            // 0..127
+    const uint32_t tempty0 = (G == 2) ? mapa_rank(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
+    uint32_t tile_ctr = 0;
+    for (long long u = worker; u < p.total_units; u += nworkers) {
+      int mb, img;
+      decode_unit(p, u, mb, img);
+      const long long row = (long long)mb * (kTileM * G) + rank * kTileM + et;
+      float best = INFINITY;
+      for (int t = 0; t < p.nt; ++t, ++tile_ctr) {
+        const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
+        const int width = (t == p.nt - 1) ? p.wlast : p.wmain;
+        const int valid = min(width, p.P - t * p.wmain);
+        const long long col0 = (long long)img * p.P + t * p.wmain;
+        float* bn = s_bn2 + buf * kMaxN;
+        for (int c = eidx; c < width; c += 128) bn[c] = (c < valid) ? __ldg(p.bn2 + col0 + c) : INFINITY;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(smem_u32(&tfull_bar[buf]), tphase, p.err, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * kMaxN + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < width; c0 += 32) {
+          uint32_t v0[16], v1[16];
+          const bool two = (c0 + 16 < width);
+          AC_TMEM_LD16(taddr + c0, v0);
+          if (two) AC_TMEM_LD16(taddr + c0 + 16, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) best = fminf(best, fmaf(-2.f, __uint_as_float(v0[i]), bn[c0 + i]));
+          if (two) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) best = fminf(best, fmaf(-2.f, __uint_as_float(v1[i]), bn[c0 + 16 + i]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (G == 2) mbar_arrive_cluster(tempty0 + buf * 8);
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + buf * 8) : "memory");
+        }
+      }
+      if (row < p.Mq) {
+        const float d2 = best + __ldg(p.qn2 + row);
+        p.dmin[(long long)img * p.Mq + row] = sqrtf(fmaxf(d2, 0.f));
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  if (G == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<G>(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || !ptr) return nullptr;
+  fn = (PFN_encodeTiled)ptr;
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* base, long long rows, int D, int box_rows, bool bf16) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return AC_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = 1000 + (int)r; return AC_ERR_CUDA; }
+  return AC_OK;
+}
+
+static uint32_t make_idesc(int M, int N, bool bf16) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // accumulator format: F32
+  d |= (bf16 ? 1u : 0u) << 7;         // A format
+  d |= (bf16 ? 1u : 0u) << 10;        // B format
+  // bits 13/14: no negate; bits 15/16: A and B K-major
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+static int g_tc_cta_group = 2;   // test hook (ac_debug_set): 1 = single-CTA MMAs, 2 = CTA pairs
+static int g_tc_gm = 8;
+
+template <int G, int kStages>
+static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {
+  constexpr int kBRows = kMaxN / G;
+  constexpr size_t kStageBytes = (size_t)kTileM * kBlockK * 2 + (size_t)kBRows * kBlockK * 2;
+  const size_t smem = 1024 + kStages * kStageBytes + 2 * kMaxN * sizeof(float) + (2 * kStages + 4) * 8 + 16;
+  auto kern = mindist_tc_kernel<G, kStages>;
+  AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long max_workers = (G == 2) ? num_sms / 2 : num_sms;
+  const int workers = (int)std::min<long long>(max_workers, prm.total_units);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * G);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AC_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
+  return AC_OK;
+}
+
+int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long long Mq, const void* Bhi, const void* Blo,
+                      const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int* err_flag, cudaStream_t st) {
+  const bool bf16 = (precision == AC_PREC_BF16 || precision == AC_PREC_BF16X3);
+  const bool x3 = (precision == AC_PREC_F16X3 || precision == AC_PREC_BF16X3);
+  if (D % 8 != 0) return AC_ERR_UNSUPPORTED;  // TMA needs a 16-byte row pitch
+  if (x3 && (!Qlo || !Blo)) return AC_ERR_INVALID;
+  const int G = g_tc_cta_group;
+  TcParams prm;
+  memset(&prm, 0, sizeof(prm));
+  // tile widths inside one bank image: multiples of 16, <= 256, as even as possible
+  int nt = ceil_div(P, kMaxN);
+  int wmain = std::min(kMaxN, ceil_div(ceil_div(P, nt), 16) * 16);
+  nt = ceil_div(P, wmain);
+  const int wlast = ceil_div(P - (nt - 1) * wmain, 16) * 16;
+  prm.nt = nt; prm.wmain = wmain; prm.wlast = wlast;
+  prm.qn2 = Qn2; prm.bn2 = Bn2; prm.dmin = dmin; prm.err = err_flag;
+  prm.Mq = Mq; prm.nb_img = nb_img; prm.P = P; prm.D = D;
+  prm.nkb = ceil_div(D, kBlockK);
+  prm.nseg = x3 ? 3 : 1;
+  prm.n_mblocks = (int)ceil_div64(Mq, (long long)kTileM * G);
+  prm.GM = g_tc_gm;
+  prm.total_units = (long long)prm.n_mblocks * nb_img;
+  prm.idesc_main = make_idesc(kTileM * G, wmain, bf16);
+  prm.idesc_last = make_idesc(kTileM * G, wlast, bf16);
+  const long long brows = (long long)nb_img * P;
+  int rc;
+  if ((rc = make_map(&prm.mapA[0], Qhi, Mq, D, kTileM, bf16))) return rc;
+  if ((rc = make_map(&prm.mapBmain[0], Bhi, brows, D, wmain / G, bf16))) return rc;
+  if ((rc = make_map(&prm.mapBlast[0], Bhi, brows, D, wlast / G, bf16))) return rc;
+  if (x3) {
+    if ((rc = make_map(&prm.mapA[1], Qlo, Mq, D, kTileM, bf16))) return rc;
+    if ((rc = make_map(&prm.mapBmain[1], Blo, brows, D, wmain / G, bf16))) return rc;
+    if ((rc = make_map(&prm.mapBlast[1], Blo, brows, D, wlast / G, bf16))) return rc;
+  } else {
+    prm.mapA[1] = prm.mapA[0]; prm.mapBmain[1] = prm.mapBmain[0]; prm.mapBlast[1] = prm.mapBlast[0];
+  }
+  int dev = 0, num_sms = 0;
+  AC_CUDA(cudaGetDevice(&dev));
+  AC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (G == 2) return launch_tc<2, 6>(prm, num_sms, st);
+  return launch_tc<1, 4>(prm, num_sms, st);
+}
+
+int launch_mindist_simt(const float* Q, long long Mq, const float* Bk, int nb_img, int P, int D, float* dmin, cudaStream_t st);
+
+}  // namespace ac
+
+using namespace ac;
+
+// test / tuning hook (not part of the public header): key 0 = cta group (1|2), key 1 = M-blocks per raster group
+extern "C" int ac_debug_set(int key, int value) {
+  if (key == 0 && (value == 1 || value == 2)) { g_tc_cta_group = value; return AC_OK; }
+  if (key == 1 && value >= 1) { g_tc_gm = value; return AC_OK; }
+  return AC_ERR_INVALID;
+}
+
+extern "C" size_t ac_min_dist_workspace_bytes(int64_t Mq, int nb_img, int P, int D, int precision) {
+  (void)Mq; (void)nb_img; (void)P; (void)D; (void)precision;
+  return 256;  // pipeline-watchdog flag
+}
+
+extern "C" int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
+                           const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, void* ws, size_t ws_bytes,
+                           ac_stream_t stream) {
+  if (!Qhi || !Bhi || !dmin || Mq < 0 || nb_img < 1 || P < 1 || D < 1) return AC_ERR_INVALID;
+  if (precision < AC_PREC_F16 || precision > AC_PREC_F32) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (Mq == 0) return AC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == AC_PREC_F32)
+    return launch_mindist_simt((const float*)Qhi, Mq, (const float*)Bhi, nb_img, P, D, dmin, st);
+  if (!Qn2 || !Bn2) return AC_ERR_INVALID;
+  if (!ws || ws_bytes < 256) return AC_ERR_WORKSPACE;
+  AC_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+  return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, dmin, (int*)ws, st);
+}

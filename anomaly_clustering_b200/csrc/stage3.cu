@@ -1,0 +1,261 @@
+// Stage 2 tail + stage 3: per-image-min reduction -> w, tau-softmax alpha, weighted embedding X,
+// image-to-image Euclidean matrix.  All HBM-bound and tiny next to the distance GEMM.
+//
+// Reference lines replaced:
+//   ac_reduce_weights  models/patchcore/utils.py:227 (mean over j != i) / :236 (min over j)
+//   ac_alpha           models/patchcore/utils.py:246-255, 266-275
+//   ac_weighted_embed  examples/main.py:294-296
+//   ac_pairwise_l2     examples/test.py:193-195 (Ward's internal pdist)
+#include "common.cuh"
+#include <math.h>
+#include <vector>
+
+namespace ac {
+
+thread_local int g_last_cuda_error = 0;
+
+int check_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e);
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e);
+  return major == 10 ? AC_OK : AC_ERR_DEVICE;
+}
+
+// one thread per query row; dmin is [nb_img, Mq] so consecutive threads read consecutive addresses
+__global__ void __launch_bounds__(256) reduce_weights_kernel(const float* __restrict__ dmin, long long Mq, int nb_img, int Pq,
+                                                             const int* __restrict__ q_self, int mode, float* __restrict__ w) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= Mq) return;
+  const int self = q_self ? q_self[r / Pq] : -1;
+  if (mode == AC_REDUCE_MEAN) {
+    float s = 0.f;
+    int cnt = 0;
+    for (int j = 0; j < nb_img; ++j) {
+      if (j == self) continue;
+      s += __ldg(dmin + (long long)j * Mq + r);  // same left-to-right order as torch.mean over the cat'ed columns
+      ++cnt;
+    }
+    w[r] = cnt > 0 ? s / (float)cnt : nanf("");
+  } else {
+    float m = INFINITY;
+    for (int j = 0; j < nb_img; ++j) {
+      if (j == self) continue;
+      m = fminf(m, __ldg(dmin + (long long)j * Mq + r));
+    }
+    w[r] = m;
+  }
+}
+
+// one CTA per image, all taus in one pass; float64 like the reference
+struct TauTable { double v[64]; };
+
+__global__ void __launch_bounds__(256) alpha_kernel(const float* __restrict__ w, int N, int P, TauTable taus, int T,
+                                                    double* __restrict__ a64, float* __restrict__ a32) {
+  const int i = blockIdx.x;
+  const float* wi = w + (long long)i * P;
+  __shared__ double red[8];
+  __shared__ double s_bcast;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+  // row max (shared by every tau)
+  float m = -INFINITY;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) m = fmaxf(m, wi[p]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = (double)m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mm = red[0];
+    for (int k = 1; k < nw; ++k) mm = fmax(mm, red[k]);
+    s_bcast = mm;
+  }
+  __syncthreads();
+  const double wmax = s_bcast;
+
+  for (int t = 0; t < T; ++t) {
+    const double tau = taus.v[t];
+    const bool onehot = (tau == 0.0);  // math.isclose(tau, 0) with the default rel_tol is true only for tau == 0
+    const double inv = onehot ? 0.0 : 1.0 / tau;
+    double s = 0.0;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      const double x = (double)wi[p];
+      s += onehot ? (x == wmax ? 1.0 : 0.0) : exp(inv * (x - wmax));
+    }
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0;
+      for (int k = 0; k < nw; ++k) tot += red[k];
+      s_bcast = tot;
+    }
+    __syncthreads();
+    const double tot = s_bcast;
+    const long long base = ((long long)t * N + i) * P;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      const double x = (double)wi[p];
+      const double e = onehot ? (x == wmax ? 1.0 : 0.0) : exp(inv * (x - wmax));
+      const double a = e / tot;
+      if (a64) a64[base + p] = a;
+      if (a32) a32[base + p] = (float)a;
+    }
+    __syncthreads();
+  }
+}
+
+// X[i, d] = sum_p alpha[i,p] * Z[i,p,d]; grid (ceil(D / (128*4)), N); each thread owns 4 columns
+__global__ void __launch_bounds__(128) weighted_embed_kernel(const float* __restrict__ alpha, const float* __restrict__ Z, int N, int P,
+                                                             int D, float* __restrict__ X) {
+  extern __shared__ float s_alpha[];
+  const int i = blockIdx.y;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) s_alpha[p] = alpha[(long long)i * P + p];
+  __syncthreads();
+  const int d0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (d0 >= D) return;
+  const float* zi = Z + (long long)i * P * D;
+  if (d0 + 3 < D && (D & 3) == 0) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) {
+      const float a = s_alpha[p];
+      const float4 z = __ldg(reinterpret_cast<const float4*>(zi + (long long)p * D + d0));
+      acc.x = fmaf(a, z.x, acc.x);
+      acc.y = fmaf(a, z.y, acc.y);
+      acc.z = fmaf(a, z.z, acc.z);
+      acc.w = fmaf(a, z.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(X + (long long)i * D + d0) = acc;
+  } else {
+    for (int d = d0; d < min(D, d0 + 4); ++d) {
+      float acc = 0.f;
+      for (int p = 0; p < P; ++p) acc = fmaf(s_alpha[p], __ldg(zi + (long long)p * D + d), acc);
+      X[(long long)i * D + d] = acc;
+    }
+  }
+}
+
+// Dmat[i,j] = sqrt(sum_d (X[i,d]-X[j,d])^2): 32x32 output tile per CTA, 2x2 per thread... kept simple:
+// 16x16 threads, each computes a 2x2 micro-tile, D walked in chunks of 32 through shared memory.
+__global__ void __launch_bounds__(256) pairwise_l2_kernel(const float* __restrict__ X, int N, int D, float* __restrict__ Dm) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+  if (bj < bi) return;  // upper triangle only; mirrored on store
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      const int d = d0 + c;
+      sa[r][c] = (bi + r < N && d < D) ? __ldg(X + (long long)(bi + r) * D + d) : 0.f;
+      sb[r][c] = (bj + r < N && d < D) ? __ldg(X + (long long)(bj + r) * D + d) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const float a0 = sa[ty][c], a1 = sa[ty + 16][c];
+      const float b0 = sb[tx][c], b1 = sb[tx + 16][c];
+      float t;
+      t = a0 - b0; acc[0][0] = fmaf(t, t, acc[0][0]);
+      t = a0 - b1; acc[0][1] = fmaf(t, t, acc[0][1]);
+      t = a1 - b0; acc[1][0] = fmaf(t, t, acc[1][0]);
+      t = a1 - b1; acc[1][1] = fmaf(t, t, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int i = bi + ty + 16 * u, j = bj + tx + 16 * v;
+      if (i < N && j < N) {
+        const float d = (i == j) ? 0.f : sqrtf(acc[u][v]);
+        if (j >= i) {
+          Dm[(long long)i * N + j] = d;
+          Dm[(long long)j * N + i] = d;
+        }
+      }
+    }
+}
+
+}  // namespace ac
+
+using namespace ac;
+
+extern "C" int ac_version(void) { return 100; }
+
+extern "C" const char* ac_strerror(int code) {
+  switch (code) {
+    case AC_OK: return "ok";
+    case AC_ERR_INVALID: return "invalid argument";
+    case AC_ERR_UNSUPPORTED: return "unsupported shape for this kernel";
+    case AC_ERR_DEVICE: return "device is not sm_100 (B200); libac_b200 has no other code path";
+    case AC_ERR_CUDA: return "CUDA call failed (see ac_last_cuda_error)";
+    case AC_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int ac_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" int ac_device_ok(int dev) {
+  int major = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e);
+  return major == 10 ? AC_OK : AC_ERR_DEVICE;
+}
+
+extern "C" int ac_reduce_weights(const float* dmin, int64_t Mq, int nb_img, int Pq, const int32_t* q_self, int mode, float* w,
+                                 ac_stream_t stream) {
+  if (!dmin || !w || Mq < 0 || nb_img < 1 || Pq < 1) return AC_ERR_INVALID;
+  if (mode != AC_REDUCE_MEAN && mode != AC_REDUCE_MIN) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (Mq == 0) return AC_OK;
+  reduce_weights_kernel<<<(unsigned)((Mq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dmin, Mq, nb_img, Pq, q_self, mode, w);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+extern "C" int ac_alpha(const float* w, int N, int P, const double* taus_host, int T, double* alpha64, float* alpha32,
+                        ac_stream_t stream) {
+  if (!w || !taus_host || N < 0 || P < 1 || T < 1 || T > 64) return AC_ERR_INVALID;
+  if (!alpha64 && !alpha32) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (N == 0) return AC_OK;
+  TauTable tt;  // <= 64 taus travel by value as a kernel parameter: re-entrant, no allocation, no sync
+  for (int t = 0; t < T; ++t) tt.v[t] = taus_host[t];
+  for (int t = T; t < 64; ++t) tt.v[t] = 1.0;
+  alpha_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(w, N, P, tt, T, alpha64, alpha32);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+extern "C" int ac_weighted_embed(const float* alpha, const float* Z, int N, int P, int D, float* X, ac_stream_t stream) {
+  if (!alpha || !Z || !X || N < 0 || P < 1 || D < 1) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (N == 0) return AC_OK;
+  if ((size_t)P * sizeof(float) > 200 * 1024) return AC_ERR_UNSUPPORTED;
+  auto kern = weighted_embed_kernel;
+  const size_t smem = (size_t)P * sizeof(float);
+  if (smem > 48 * 1024) AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(D, 128 * 4), N);
+  kern<<<grid, 128, smem, (cudaStream_t)stream>>>(alpha, Z, N, P, D, X);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+extern "C" int ac_pairwise_l2(const float* X, int N, int D, float* Dmat, ac_stream_t stream) {
+  if (!X || !Dmat || N < 0 || D < 1) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (N == 0) return AC_OK;
+  dim3 grid(ceil_div(N, 32), ceil_div(N, 32));
+  pairwise_l2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, Dmat);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}

@@ -1,0 +1,210 @@
+"""Torch-tensor wrappers over the C ABI (include/ac_b200.h).  PyTorch is plumbing here: it owns
+device memory and streams; every computation happens in libac_b200.so."""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AcLayer, check
+
+_OP_DTYPES = {"f16": (torch.float16, _lib.AC_DT_F16), "bf16": (torch.bfloat16, _lib.AC_DT_BF16)}
+_TORCH_TO_AC = {torch.float32: _lib.AC_DT_F32, torch.float16: _lib.AC_DT_F16, torch.bfloat16: _lib.AC_DT_BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("libac_b200 operates on CUDA tensors only (no CPU fallback)")
+
+
+def device_ok(dev: Optional[int] = None) -> bool:
+    lib = _lib.load()
+    if dev is None:
+        dev = torch.cuda.current_device()
+    return lib.ac_device_ok(int(dev)) == 0
+
+
+def feature_view(f: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] stays; ViT block output [B,1+P,C] becomes a strided [B,C,s,s] VIEW with the CLS
+    token skipped (reference: models/patchcore/patchcore.py:377-383) -- no copy is made."""
+    if f.dim() == 3:
+        B, T, C = f.shape
+        s = int(math.sqrt(T - 1))
+        if s * s != T - 1:
+            raise ValueError("token count minus CLS is not a square: %d" % (T - 1))
+        return f[:, 1:, :].unflatten(1, (s, s)).permute(0, 3, 1, 2)
+    if f.dim() != 4:
+        raise ValueError("feature must be [B,C,H,W] or [B,1+P,C]")
+    return f
+
+
+def patch_grid(H: int, W: int, patchsize: int, stride: int) -> Tuple[int, int]:
+    pad = int((patchsize - 1) / 2)
+    return ((H + 2 * pad - (patchsize - 1) - 1) // stride + 1, (W + 2 * pad - (patchsize - 1) - 1) // stride + 1)
+
+
+def embed(
+    features: Sequence[torch.Tensor],
+    patchsize: int,
+    stride: int,
+    pretrain_dim: int,
+    target_dim: int,
+    layernorm: bool = True,
+    eps: float = 1e-5,
+    want_z: bool = True,
+    operand: Optional[str] = None,
+    want_lo: bool = False,
+    out_z: Optional[torch.Tensor] = None,
+    out_hi: Optional[torch.Tensor] = None,
+    out_lo: Optional[torch.Tensor] = None,
+):
+    """Fused stage 1.  Returns (Z [B*P, D] fp32 | None, Zhi | None, Zlo | None, (h, w))."""
+    lib = _lib.load()
+    views = [feature_view(f) for f in features]
+    _need_cuda(*views)
+    for v in views:
+        if v.dtype != torch.float32:
+            raise ValueError("features must be float32")
+    B = views[0].shape[0]
+    L = len(views)
+    arr = (AcLayer * L)()
+    for i, v in enumerate(views):
+        _, C, H, W = v.shape
+        sb, sc, sh, sw = v.stride()
+        arr[i] = AcLayer(v.data_ptr(), C, H, W, sb, sc, sh, sw)
+    h, w = patch_grid(views[0].shape[2], views[0].shape[3], patchsize, stride)
+    rows = B * h * w
+    dev = views[0].device
+    Z = hi = lo = None
+    if want_z:
+        Z = out_z if out_z is not None else torch.empty(rows, target_dim, dtype=torch.float32, device=dev)
+    op_code = 0
+    if operand is not None:
+        tdt, op_code = _OP_DTYPES[operand]
+        hi = out_hi if out_hi is not None else torch.empty(rows, target_dim, dtype=tdt, device=dev)
+        if want_lo:
+            lo = out_lo if out_lo is not None else torch.empty(rows, target_dim, dtype=tdt, device=dev)
+    ws_bytes = lib.ac_embed_workspace_bytes(L, B, h * w, pretrain_dim, target_dim)
+    # the concat scratch is only touched when the Aggregator cannot be fused; allocate lazily sized
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rc = lib.ac_embed(arr, L, B, patchsize, stride, pretrain_dim, target_dim, int(layernorm), float(eps), _ptr(Z), _ptr(hi),
+                      _ptr(lo), op_code, _ptr(ws), ws_bytes, _stream())
+    check(rc, "ac_embed")
+    return Z, hi, lo, (h, w)
+
+
+def patchify(x: torch.Tensor, patchsize: int, stride: int):
+    lib = _lib.load()
+    _need_cuda(x)
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    h, w = patch_grid(H, W, patchsize, stride)
+    out = torch.empty(B, h * w, C, patchsize, patchsize, dtype=torch.float32, device=x.device)
+    grid = (ctypes.c_int * 2)()
+    check(lib.ac_patchify(_ptr(x), B, C, H, W, patchsize, stride, _ptr(out), grid, _stream()), "ac_patchify")
+    return out, [int(grid[0]), int(grid[1])]
+
+
+def adaptive_pool1d(x: torch.Tensor, out_dim: int) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(x)
+    x2 = x.reshape(len(x), -1).contiguous().float()
+    out = torch.empty(x2.shape[0], out_dim, dtype=torch.float32, device=x.device)
+    check(lib.ac_adaptive_pool1d(_ptr(x2), x2.shape[0], x2.shape[1], out_dim, _ptr(out), _stream()), "ac_adaptive_pool1d")
+    return out
+
+
+def split_operand(x: torch.Tensor, operand: str, want_lo: bool):
+    lib = _lib.load()
+    _need_cuda(x)
+    x = x.contiguous()
+    tdt, code = _OP_DTYPES[operand]
+    hi = torch.empty(x.shape, dtype=tdt, device=x.device)
+    lo = torch.empty(x.shape, dtype=tdt, device=x.device) if want_lo else None
+    check(lib.ac_split_operand(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), code, _stream()), "ac_split_operand")
+    return hi, lo
+
+
+def row_norms(A: torch.Tensor, A2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(A, A2)
+    assert A.dim() == 2 and A.is_contiguous()
+    out = torch.empty(A.shape[0], dtype=torch.float32, device=A.device)
+    check(lib.ac_row_norms(_ptr(A), _ptr(A2), _TORCH_TO_AC[A.dtype], A.shape[0], A.shape[1], _ptr(out), _stream()), "ac_row_norms")
+    return out
+
+
+def min_dist(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dmin [nb_img, Mq]: per bank image, distance of each query row to its nearest bank row."""
+    lib = _lib.load()
+    _need_cuda(Qhi, Bhi)
+    prec = _lib.PRECISIONS[precision]
+    Mq, D = Qhi.shape
+    assert Bhi.shape == (nb_img * P, D), (Bhi.shape, nb_img, P, D)
+    assert Qhi.is_contiguous() and Bhi.is_contiguous()
+    dmin = out if out is not None else torch.empty(nb_img, Mq, dtype=torch.float32, device=Qhi.device)
+    ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
+    rc = lib.ac_min_dist(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec, _ptr(dmin),
+                         _ptr(ws), ws_bytes, _stream())
+    check(rc, "ac_min_dist")
+    return dmin
+
+
+def reduce_weights(dmin: torch.Tensor, Pq: int, q_self: Optional[torch.Tensor], mode: str) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(dmin, q_self)
+    nb_img, Mq = dmin.shape
+    w = torch.empty(Mq, dtype=torch.float32, device=dmin.device)
+    m = _lib.AC_REDUCE_MEAN if mode == "mean" else _lib.AC_REDUCE_MIN
+    if q_self is not None:
+        assert q_self.dtype == torch.int32 and q_self.numel() * Pq >= Mq
+    check(lib.ac_reduce_weights(_ptr(dmin), Mq, nb_img, Pq, _ptr(q_self), m, _ptr(w), _stream()), "ac_reduce_weights")
+    return w
+
+
+def alpha(w: torch.Tensor, taus: Sequence[float], want64: bool = True, want32: bool = True):
+    """w [N,P] fp32 -> (alpha64 [T,N,P] | None, alpha32 [T,N,P] | None)."""
+    lib = _lib.load()
+    _need_cuda(w)
+    w = w.contiguous()
+    N, P = w.shape
+    T = len(taus)
+    a64 = torch.empty(T, N, P, dtype=torch.float64, device=w.device) if want64 else None
+    a32 = torch.empty(T, N, P, dtype=torch.float32, device=w.device) if want32 else None
+    tarr = (ctypes.c_double * T)(*[float(t) for t in taus])
+    check(lib.ac_alpha(_ptr(w), N, P, tarr, T, _ptr(a64), _ptr(a32), _stream()), "ac_alpha")
+    return a64, a32
+
+
+def weighted_embed(alpha32: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(alpha32, Z)
+    N, P, D = Z.shape
+    a = alpha32.reshape(N, P).contiguous().float()
+    assert Z.is_contiguous() and Z.dtype == torch.float32
+    X = torch.empty(N, D, dtype=torch.float32, device=Z.device)
+    check(lib.ac_weighted_embed(_ptr(a), _ptr(Z), N, P, D, _ptr(X), _stream()), "ac_weighted_embed")
+    return X
+
+
+def pairwise_l2(X: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(X)
+    X = X.contiguous().float()
+    N, D = X.shape
+    out = torch.empty(N, N, dtype=torch.float32, device=X.device)
+    check(lib.ac_pairwise_l2(_ptr(X), N, D, _ptr(out), _stream()), "ac_pairwise_l2")
+    return out

@@ -1,0 +1,173 @@
+"""Feature maps -> (Z, w, alpha, X, Dmat) on one B200, and its query-sharded multi-GPU form.
+
+This is the device-resident replacement of the body of make_category_data
+(reference: Anomaly-Clustering/examples/main.py:266-296) from the hooked backbone features on:
+
+    Z      = AnomalyClusteringCore.embed(...)                      main.py:266-267
+    alpha  = Matrix_Alpha_Unsupervised / _Supervised / average     main.py:281-291
+    X      = bmm(alpha, Z)                                         main.py:294-296
+    Dmat   = pairwise Euclid on X (Ward's input)                   test.py:193-195
+
+Nothing bounces through the host (the reference copies every patch row to numpy and back,
+patchcore.py:358-361 + main.py:267) and one min-distance pass serves every tau.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+_OPERAND_OF = {"f16": ("f16", False), "bf16": ("bf16", False), "f16x3": ("f16", True), "bf16x3": ("bf16", True), "f32": (None, False)}
+
+
+@dataclass
+class PatchSet:
+    """Embedded images: fp32 Z plus the tensor-core operands and their squared norms."""
+
+    n_img: int
+    P: int
+    D: int
+    grid: Tuple[int, int]
+    Z: Optional[torch.Tensor] = None      # [n_img*P, D] fp32
+    hi: Optional[torch.Tensor] = None     # [n_img*P, D] f16 | bf16
+    lo: Optional[torch.Tensor] = None
+    n2: Optional[torch.Tensor] = None     # [n_img*P] fp32 squared norms of the operand (hi [+ lo])
+
+
+@dataclass
+class PathResult:
+    Z: torch.Tensor                       # [N, P, D] fp32
+    w: Optional[torch.Tensor]             # [N, P] fp32 (None in 'average' mode)
+    alpha64: torch.Tensor                 # [T, N, P] float64  (reference dtype, utils.py:246)
+    alpha32: torch.Tensor                 # [T, N, P] float32  (main.py:294 `.float()`)
+    X: torch.Tensor                       # [T, N, D] fp32
+    Dmat: torch.Tensor                    # [T, N, N] fp32
+    taus: List[float] = field(default_factory=list)
+    grid: Tuple[int, int] = (0, 0)
+
+
+def embed_images(
+    features: Sequence[torch.Tensor],
+    patchsize: int,
+    stride: int,
+    pretrain_dim: int,
+    target_dim: int,
+    precision: str = "f16",
+    want_z: bool = True,
+    layernorm: bool = True,
+    batch: int = 16,
+) -> PatchSet:
+    """Stage 1 for a set of images, `batch` images per launch so that the LayerNorm statistics pass
+    and the fused embed kernel both find the feature maps in L2."""
+    operand, want_lo = _OPERAND_OF[precision]
+    views = [ops.feature_view(f) for f in features]
+    N = views[0].shape[0]
+    h, w = ops.patch_grid(views[0].shape[2], views[0].shape[3], patchsize, stride)
+    P = h * w
+    dev = views[0].device
+    need_z = want_z or operand is None
+    Z = torch.empty(N * P, target_dim, dtype=torch.float32, device=dev) if need_z else None
+    hi = lo = None
+    if operand is not None:
+        tdt = torch.float16 if operand == "f16" else torch.bfloat16
+        hi = torch.empty(N * P, target_dim, dtype=tdt, device=dev)
+        lo = torch.empty(N * P, target_dim, dtype=tdt, device=dev) if want_lo else None
+    for b0 in range(0, N, batch):
+        b1 = min(N, b0 + batch)
+        sl = slice(b0 * P, b1 * P)
+        ops.embed(
+            [v[b0:b1] for v in views], patchsize, stride, pretrain_dim, target_dim, layernorm=layernorm,
+            want_z=need_z, operand=operand, want_lo=want_lo,
+            out_z=None if Z is None else Z[sl], out_hi=None if hi is None else hi[sl], out_lo=None if lo is None else lo[sl],
+        )
+    ps = PatchSet(n_img=N, P=P, D=target_dim, grid=(h, w), Z=Z, hi=hi, lo=lo)
+    if operand is not None:
+        ps.n2 = ops.row_norms(hi, lo)
+    return ps
+
+
+def patchset_from_Z(Z: torch.Tensor, precision: str = "f16") -> PatchSet:
+    """Wrap an existing [N,P,D] fp32 embedding (e.g. the reference's `Z`) for the distance stage."""
+    N, P, D = Z.shape
+    Zf = Z.reshape(N * P, D).contiguous().float()
+    operand, want_lo = _OPERAND_OF[precision]
+    ps = PatchSet(n_img=N, P=P, D=D, grid=(0, 0), Z=Zf)
+    if operand is not None:
+        ps.hi, ps.lo = ops.split_operand(Zf, operand, want_lo)
+        ps.n2 = ops.row_norms(ps.hi, ps.lo)
+    return ps
+
+
+def min_distance_weights(
+    q: PatchSet,
+    bank: PatchSet,
+    mode: str,
+    precision: str = "f16",
+    q_self: Optional[torch.Tensor] = None,
+    return_dmin: bool = False,
+):
+    """Stage 2: w [Nq, P].  mode 'unsupervised' = mean over bank images != self (utils.py:222-227),
+    'supervised' = min over bank images (utils.py:230-237).  q_self[i] = bank index of query image i."""
+    if precision == "f32":
+        dmin = ops.min_dist(q.Z, None, None, bank.Z, None, None, bank.n_img, bank.P, "f32")
+    else:
+        dmin = ops.min_dist(q.hi, q.lo, q.n2, bank.hi, bank.lo, bank.n2, bank.n_img, bank.P, precision)
+    if mode == "unsupervised":
+        if q_self is None:
+            q_self = torch.arange(q.n_img, dtype=torch.int32, device=dmin.device)
+        w = ops.reduce_weights(dmin, q.P, q_self, "mean")
+    elif mode == "supervised":
+        w = ops.reduce_weights(dmin, q.P, None, "min")
+    else:
+        raise ValueError(mode)
+    w = w.reshape(q.n_img, q.P)
+    return (w, dmin) if return_dmin else w
+
+
+def alpha_X_dist(ps: PatchSet, w: Optional[torch.Tensor], taus: Sequence[float]):
+    """Stage 3 for every tau from one w.  w=None -> 'average' mode (main.py:290-291)."""
+    N, P, D = ps.n_img, ps.P, ps.D
+    dev = ps.Z.device
+    if w is None:
+        a32 = torch.full((1, N, P), 1.0 / P, dtype=torch.float32, device=dev)
+        a64 = a32.double()
+        taus = [float("nan")]
+    else:
+        a64, a32 = ops.alpha(w, taus)
+    Z3 = ps.Z.reshape(N, P, D)
+    X = torch.stack([ops.weighted_embed(a32[t], Z3) for t in range(a32.shape[0])])
+    Dm = torch.stack([ops.pairwise_l2(X[t]) for t in range(a32.shape[0])])
+    return a64, a32, X, Dm
+
+
+def run_path(
+    features: Sequence[torch.Tensor],
+    patchsize: int = 3,
+    stride: int = 1,
+    pretrain_dim: int = 1024,
+    target_dim: int = 1024,
+    mode: str = "unsupervised",
+    taus: Sequence[float] = (1.0,),
+    bank_features: Optional[Sequence[torch.Tensor]] = None,
+    precision: str = "f16",
+    layernorm: bool = True,
+) -> PathResult:
+    """Single-GPU hot path: hooked features (device tensors) -> PathResult (device tensors)."""
+    q = embed_images(features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=True, layernorm=layernorm)
+    w = None
+    if mode == "unsupervised":
+        w = min_distance_weights(q, q, "unsupervised", precision)
+    elif mode == "supervised":
+        if bank_features is None:
+            raise ValueError("supervised mode needs bank_features (the normal training images)")
+        bank = embed_images(bank_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=False,
+                            layernorm=layernorm)
+        w = min_distance_weights(q, bank, "supervised", precision)
+    elif mode != "average":
+        raise ValueError("mode must be unsupervised | supervised | average")
+    a64, a32, X, Dm = alpha_X_dist(q, w, list(taus))
+    return PathResult(Z=q.Z.reshape(q.n_img, q.P, q.D), w=w, alpha64=a64, alpha32=a32, X=X, Dmat=Dm,
+                      taus=list(taus), grid=q.grid)

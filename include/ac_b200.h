@@ -1,0 +1,150 @@
+/*
+ * ac_b200.h -- C ABI of libac_b200.so: the B200-native (sm_100a) embedding-to-distance path of
+ * KevinWangHP/Anomaly-Clustering.
+ *
+ * The reference is 100 % Python: it has no FFI for this path, the "interface" is the Python call
+ * surface of Anomaly-Clustering/models/patchcore/{patchcore,common,utils}.py and examples/main.py.
+ * Each entry point below names the reference lines it replaces.  A maintainer binds these with
+ * ctypes; anomaly_clustering_b200/_lib.py is exactly that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns every buffer,
+ *     including the workspace; the library allocates nothing persistent and keeps no global state;
+ *   - every call is asynchronous and ordered on `stream` (a cudaStream_t); no hidden synchronisation;
+ *   - return value: 0 on success, a negative AC_ERR_* code otherwise (never throws, never aborts);
+ *   - there is NO CPU fallback: on anything that is not compute capability 10.x the calls fail with
+ *     AC_ERR_DEVICE.
+ */
+#ifndef AC_B200_H
+#define AC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AC_OK 0
+#define AC_ERR_INVALID (-1)     /* bad argument (null pointer, non-positive size, ...)            */
+#define AC_ERR_UNSUPPORTED (-2) /* shape outside what the kernels implement (stated per function) */
+#define AC_ERR_DEVICE (-3)      /* current device is not sm_100 (B200)                            */
+#define AC_ERR_CUDA (-4)        /* a CUDA runtime / driver call failed (see ac_last_cuda_error)   */
+#define AC_ERR_WORKSPACE (-5)   /* workspace too small                                            */
+
+/* operand element types (for the tensor-core operands and ac_row_norms) */
+#define AC_DT_F32 0
+#define AC_DT_F16 1
+#define AC_DT_BF16 2
+
+/* precision modes of ac_min_dist */
+#define AC_PREC_F16 0    /* tcgen05 kind::f16, fp16 operands, fp32 accumulate (1 MMA pass)          */
+#define AC_PREC_BF16 1   /* tcgen05 kind::f16, bf16 operands                                        */
+#define AC_PREC_F16X3 2  /* split fp16 hi+lo, hi*hi + lo*hi + hi*lo in one accumulator (3 passes)   */
+#define AC_PREC_BF16X3 3 /* split bf16 hi+lo, 3 passes                                              */
+#define AC_PREC_F32 4    /* exact fp32 SIMT kernel, sum (x-y)^2, no tensor cores                    */
+
+/* reduce modes of ac_reduce_weights */
+#define AC_REDUCE_MEAN 0 /* unsupervised: mean over bank images (self excluded)  utils.py:227 */
+#define AC_REDUCE_MIN 1  /* supervised:   min over bank images                   utils.py:236 */
+
+typedef void* ac_stream_t; /* cudaStream_t */
+
+/* One hooked backbone feature map, read IN PLACE through strides (elements, not bytes):
+ * CNN maps [B,C,H,W] contiguous: sb=C*H*W, sc=H*W, sh=W, sw=1.
+ * ViT block outputs [B,1+P,C] (models/patchcore/patchcore.py:377-383 drops CLS and permutes):
+ *   ptr = tokens + C (skips CLS), sb=(1+P)*C, sc=1, sh=W*C, sw=C -- no permuted copy is made. */
+typedef struct {
+  const float* ptr;
+  int32_t C, H, W;
+  int64_t sb, sc, sh, sw;
+} ac_layer_t;
+
+/* ---- library / device ------------------------------------------------------------------------ */
+int ac_version(void);
+const char* ac_strerror(int code);
+/* 0 if device `dev` is compute capability 10.x, AC_ERR_DEVICE otherwise. */
+int ac_device_ok(int dev);
+/* cudaError_t of the last failing CUDA call made by this library on this thread (0 if none). */
+int ac_last_cuda_error(void);
+
+/* ---- stage 1: feature maps -> patch embeddings Z ----------------------------------------------
+ * Replaces AnomalyClusteringCore._embed after the backbone (models/patchcore/patchcore.py:368-431):
+ * whole-map LayerNorm (:384-385), PatchMaker.patchify (:439-465), cross-layer bilinear resize
+ * (:398-421), Preprocessing/MeanMapper (models/patchcore/common.py:145-170), Aggregator (:173-183),
+ * in one fused kernel (+ a per-image statistics pre-pass).  No im2col tensor is materialised.
+ *
+ *   layers_host : HOST array of L descriptors
+ *   Z           : [B*P, D] fp32 or NULL         P = patch grid of layer 0
+ *   Zhi, Zlo    : [B*P, D] op_dtype (AC_DT_F16/AC_DT_BF16) or NULL: hi = round(Z), lo = round(Z-hi),
+ *                 the tensor-core operands of ac_min_dist
+ *   layernorm   : 1 = AnomalyClusteringCore._embed, 0 = PatchCore._embed (patchcore.py:92-146)
+ * Workspace: ac_embed_workspace_bytes(L, B, P, Dp, D). */
+size_t ac_embed_workspace_bytes(int L, int B, int64_t P, int Dp, int D);
+int ac_embed(const ac_layer_t* layers_host, int L, int B, int patchsize, int stride, int Dp, int D,
+             int layernorm, float eps, float* Z, void* Zhi, void* Zlo, int op_dtype, void* ws,
+             size_t ws_bytes, ac_stream_t stream);
+
+/* PatchMaker.patchify standalone (models/patchcore/patchcore.py:439-465):
+ * x [B,C,H,W] contiguous -> out [B, h*w, C, k, k]; grid_host[2] receives (h, w). */
+int ac_patchify(const float* x, int B, int C, int H, int W, int patchsize, int stride, float* out,
+                int* grid_host, ac_stream_t stream);
+
+/* F.adaptive_avg_pool1d over the last axis: in [rows, Lin] -> out [rows, Lout].
+ * MeanMapper.forward (common.py:168-170) and Aggregator.forward (common.py:178-183). */
+int ac_adaptive_pool1d(const float* in, int64_t rows, int Lin, int Lout, float* out,
+                       ac_stream_t stream);
+
+/* hi = round_to(dtype, x), lo = round_to(dtype, x - hi)  (lo may be NULL).  n elements. */
+int ac_split_operand(const float* x, int64_t n, void* hi, void* lo, int dtype, ac_stream_t stream);
+
+/* n2[r] = sum_d A[r,d]^2 in fp32; A is [rows, D] of `dtype`; if A2 != NULL the row is A + A2
+ * (hi + lo operands). */
+int ac_row_norms(const void* A, const void* A2, int dtype, int64_t rows, int D, float* n2,
+                 ac_stream_t stream);
+
+/* ---- stage 2: patch-versus-bank nearest neighbour ----------------------------------------------
+ * Replaces the torch.cdist + torch.min(dim=1) loops of Weight_Distance_Unsupervised / _Supervised
+ * (models/patchcore/utils.py:222-237):
+ *   dmin[j*Mq + r] = min over the P rows q of bank image j of || Q[r] - Bank[j*P+q] ||_2
+ * computed as sqrt(max(0, |q|^2 + |b|^2 - 2 q.b)) with the dot products on the tcgen05 tensor cores
+ * (TMA-fed, fp32 accumulation in TMEM) and the per-bank-image row-min fused into the epilogue: the
+ * [Mq, nb_img*P] distance matrix never reaches HBM.  AC_PREC_F32 runs an exact SIMT kernel instead.
+ *
+ *   Qhi/Qlo [Mq, D], Bhi/Blo [nb_img*P, D] : operands of the dtype implied by `precision`
+ *             (fp32 for AC_PREC_F32; lo only for the X3 modes, else NULL)
+ *   Qn2 [Mq], Bn2 [nb_img*P] : fp32 squared norms of the operands (ac_row_norms), unused for F32
+ *   dmin [nb_img, Mq] fp32
+ * Tensor-core modes need D % 8 == 0 (TMA row pitch), else AC_ERR_UNSUPPORTED.
+ * Workspace: ac_min_dist_workspace_bytes(). */
+size_t ac_min_dist_workspace_bytes(int64_t Mq, int nb_img, int P, int D, int precision);
+int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi,
+                const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision,
+                float* dmin, void* ws, size_t ws_bytes, ac_stream_t stream);
+
+/* w[r] = mean_j dmin[j, r] over bank images j != q_self[r / Pq]   (AC_REDUCE_MEAN, utils.py:227)
+ *      = min_j  dmin[j, r]                                           (AC_REDUCE_MIN,  utils.py:236)
+ * q_self: [ceil(Mq/Pq)] int32 bank-image index of each query image, -1 or NULL = none. */
+int ac_reduce_weights(const float* dmin, int64_t Mq, int nb_img, int Pq, const int32_t* q_self,
+                      int mode, float* w, ac_stream_t stream);
+
+/* ---- stage 3 -----------------------------------------------------------------------------------
+ * alpha[t, i, :] = softmax_p(w[i, :] / tau_t) in float64, max-subtracted (identical to
+ * Matrix_Alpha_* wherever the reference's exp does not overflow, utils.py:246-255); |tau| < 1e-9
+ * gives the reference's one-hot-on-max with ties split equally (:248-250).
+ * alpha64 [T,N,P] double and/or alpha32 [T,N,P] float (either may be NULL). taus_host: HOST array. */
+int ac_alpha(const float* w, int N, int P, const double* taus_host, int T, double* alpha64,
+             float* alpha32, ac_stream_t stream);
+
+/* X[i, :] = sum_p alpha[i,p] * Z[i,p,:]   (torch.bmm line, examples/main.py:294-296). */
+int ac_weighted_embed(const float* alpha, const float* Z, int N, int P, int D, float* X,
+                      ac_stream_t stream);
+
+/* Dmat[i,j] = || X[i] - X[j] ||_2, the Euclidean matrix Ward linkage consumes
+ * (examples/test.py:193-195 -> scipy pdist).  Dmat [N,N] fp32, exactly symmetric, zero diagonal. */
+int ac_pairwise_l2(const float* X, int N, int D, float* Dmat, ac_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AC_B200_H */

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds, loads, and exports exactly what include/ac_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from anomaly_clustering_b200 import build
+
+    return build.build()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "ac_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ac_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_symbols():
+    syms = header_symbols()
+    assert "ac_embed" in syms and "ac_min_dist" in syms and "ac_pairwise_l2" in syms
+    assert len(syms) >= 15
+
+
+def test_library_exports_every_header_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for s in header_symbols():
+        assert hasattr(lib, s), "missing export: " + s
+
+
+def test_binding_covers_header(lib_path):
+    from anomaly_clustering_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+    lib = _lib.load()
+    assert lib.ac_version() >= 100
+    assert lib.ac_strerror(-3).decode().startswith("device is not sm_100")
+    # workspace sizing is host-only arithmetic
+    assert lib.ac_embed_workspace_bytes(2, 4, 784, 2048, 4096) < (1 << 20)          # fused aggregator: no concat scratch
+    assert lib.ac_embed_workspace_bytes(3, 3, 100, 100, 77) > 3 * 100 * 300 * 4      # straddling windows need it
+    assert lib.ac_min_dist_workspace_bytes(1000, 10, 784, 4096, 0) >= 256
+
+
+def test_no_cpu_fallback_without_gpu(lib_path):
+    import torch
+
+    from anomaly_clustering_b200 import ops
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ValueError):
+        ops.pairwise_l2(torch.zeros(4, 8))
+
+
+def test_sass_is_blackwell_native(lib_path):
+    """tcgen05 / TMEM / TMA mnemonics must be present in the shipped SASS (B200_PROFILING.md)."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic

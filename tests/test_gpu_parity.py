@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the committed reference
+outputs.  Tolerances are the north_star's: alpha max-abs <= 1e-3, X and Dmat <= 1e-3 relative L2,
+identical Ward labels; kernel-level checks are much tighter and say so."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from anomaly_clustering_b200 import ops, pipeline, synth  # noqa: E402
+from oracle import cluster as ocluster  # noqa: E402
+from oracle import restated  # noqa: E402
+
+EMBED_CASES = ["embed_vit_small", "embed_wrn_small", "embed_ragged", "embed_k5s2", "embed_single"]
+
+
+def gload(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def test_device_is_b200():
+    assert ops.device_ok()
+
+
+# ------------------------------------------------------------------------------- stage 1
+@pytest.mark.parametrize("name", EMBED_CASES)
+def test_embed_golden(golden_dir, name):
+    g = gload(golden_dir, name)
+    feats = [torch.from_numpy(g["feat%d" % i]).cuda() for i in range(int(g["L"]))]
+    Z, hi, lo, grid = ops.embed(feats, int(g["patchsize"]), int(g["stride"]), int(g["Dp"]), int(g["D"]), operand="f16",
+                                want_lo=True)
+    err = np.abs(Z.cpu().numpy() - g["Z"]).max()
+    assert err <= 1e-5, err   # fp32 kernel vs the reference's fp32 torch ops: summation-order noise only
+    # operands: hi = fp16(Z), lo = fp16(Z - hi)
+    assert torch.equal(hi, Z.half())
+    assert torch.equal(lo, (Z - hi.float()).half())
+
+
+@pytest.mark.parametrize("layernorm", [True, False])
+def test_embed_config2_shape_vs_oracle(layernorm):
+    """DINO ViT-B/8 shape: two [B,785,768] token tensors, 2048 -> 4096 (BASELINE config 2)."""
+    feats, _ = synth.planted_features(3, [(768, 28, 28, True), (768, 28, 28, True)], seed=5)
+    want = restated.embed(feats, 3, 1, 2048, 4096, layernorm=layernorm)
+    Z, hi, _, grid = ops.embed([f.cuda() for f in feats], 3, 1, 2048, 4096, layernorm=layernorm, operand="bf16")
+    assert grid == (28, 28) and Z.shape == (3 * 784, 4096)
+    err = (Z.cpu() - want).abs().max().item()
+    assert err <= 2e-5, err
+    assert torch.equal(hi, Z.bfloat16())
+
+
+def test_embed_config1_shape_vs_oracle():
+    """WideResNet50 layer2+layer3 shape, 1024 -> 1024, incl. the 14->28 bilinear step (config 1)."""
+    feats, _ = synth.planted_features(2, [(512, 28, 28, False), (1024, 14, 14, False)], seed=6)
+    want = restated.embed(feats, 3, 1, 1024, 1024)
+    Z, _, _, grid = ops.embed([f.cuda() for f in feats], 3, 1, 1024, 1024)
+    assert grid == (28, 28)
+    err = (Z.cpu() - want).abs().max().item()
+    assert err <= 2e-5, err
+
+
+def test_embed_reads_strided_views_in_place():
+    """Non-contiguous inputs (channels-last maps, sliced batches) are read through their strides."""
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 20, 9, 11, generator=gen)
+    want = restated.embed([x[1:3]], 3, 1, 64, 64)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    Z, _, _, _ = ops.embed([xc[1:3]], 3, 1, 64, 64)
+    assert (Z.cpu() - want).abs().max().item() <= 1e-5
+
+
+def test_embed_constant_image_is_finite():
+    """zero-variance map: LayerNorm divides by sqrt(eps), no NaN (same as torch)."""
+    x = torch.ones(1, 8, 6, 6)
+    want = restated.embed([x], 3, 1, 16, 16)
+    Z, _, _, _ = ops.embed([x.cuda()], 3, 1, 16, 16)
+    assert torch.isfinite(Z).all()
+    assert (Z.cpu() - want).abs().max().item() <= 1e-5
+
+
+def test_patchify_and_pools_golden(golden_dir):
+    g = gload(golden_dir, "patchify_small")
+    x = torch.from_numpy(g["x"]).cuda()
+    for k, s in [(3, 1), (5, 2), (1, 1)]:
+        u, grid = ops.patchify(x, k, s)
+        assert grid == list(g["grid_k%d_s%d" % (k, s)])
+        assert np.array_equal(u.cpu().numpy(), g["patch_k%d_s%d" % (k, s)])  # pure data movement: bit exact
+    for key, dim in (("pre_in0", 20), ("pre_in1", 20)):
+        got = ops.adaptive_pool1d(torch.from_numpy(g[key]).cuda(), dim).cpu()
+        want = restated.preprocessing_forward([torch.from_numpy(g[key])], dim)[:, 0]
+        assert (got - want).abs().max().item() <= 1e-6
+    agg = ops.adaptive_pool1d(torch.from_numpy(g["pre_out"]).cuda(), 13).cpu().numpy()
+    assert np.abs(agg - g["agg_out"]).max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------- stage 2
+def _exact_dmin(opq, opb, n_b, P):
+    """fp64 min distance per bank image from given operands (CPU, checker only)."""
+    q = opq.double().cpu()
+    b = opb.double().cpu().reshape(n_b, P, -1)
+    out = torch.empty(n_b, q.shape[0], dtype=torch.float64)
+    for j in range(n_b):
+        out[j] = torch.cdist(q, b[j]).min(dim=1)[0]
+    return out
+
+
+def test_mindist_f32_matches_reference_weights(golden_dir):
+    g = gload(golden_dir, "alpha_small")
+    Z = torch.from_numpy(g["Z"]).cuda()
+    Zb = torch.from_numpy(g["Z_train"]).cuda()
+    q = pipeline.patchset_from_Z(Z, "f32")
+    b = pipeline.patchset_from_Z(Zb, "f32")
+    wu = pipeline.min_distance_weights(q, q, "unsupervised", "f32")
+    ws = pipeline.min_distance_weights(q, b, "supervised", "f32")
+    assert np.abs(wu.cpu().numpy() - g["w_unsup"]).max() <= 2e-5
+    assert np.abs(ws.cpu().numpy() - g["w_sup"]).max() <= 2e-5
+
+
+@pytest.mark.parametrize("precision", ["f16", "bf16", "f16x3", "bf16x3"])
+@pytest.mark.parametrize("shape", [(3, 784, 256), (4, 100, 320), (2, 36, 64), (5, 260, 128)])
+def test_mindist_tensor_core_kernel_arithmetic(precision, shape):
+    """The tcgen05 kernel against an fp64 evaluation of the SAME rounded operands: isolates kernel
+    correctness (tiling, swizzle, segmented min, masking) from operand rounding."""
+    n, P, D = shape
+    gen = torch.Generator().manual_seed(n * 1000 + P)
+    base = torch.randn(1, P, D, generator=gen)
+    Z = (base + 0.5 * torch.randn(n, P, D, generator=gen)).cuda()
+    ps = pipeline.patchset_from_Z(Z, precision)
+    dmin = ops.min_dist(ps.hi, ps.lo, ps.n2, ps.hi, ps.lo, ps.n2, n, P, precision)
+    op = ps.hi.double() + (ps.lo.double() if ps.lo is not None else 0.0)
+    want = _exact_dmin(op, op, n, P)
+    # off-diagonal (different image) entries: fp32 accumulation error only
+    got = dmin.double().cpu()
+    scale = want.max().item()
+    assert (got - want).abs().max().item() <= 2e-3 * scale + 1e-2  # d ~ sqrt(D); self-distances cancel to ~1e-2 at most
+    mask = torch.ones_like(want, dtype=torch.bool)
+    for j in range(n):
+        mask[j, j * P:(j + 1) * P] = False
+    rel = ((got - want).abs() / want.clamp_min(1e-6))[mask].max().item()
+    assert rel <= (5e-4 if "x3" not in precision else 5e-5), rel
+
+
+@pytest.mark.parametrize("precision,tol", [("f16", 3e-3), ("f16x3", 2e-4), ("f32", 1e-4)])
+def test_mindist_vs_oracle_config2_width(precision, tol):
+    """P = 784, D = 4096 (config-2 geometry), 4 query images vs 5 bank images (supervised form)."""
+    feats, _ = synth.planted_features(9, [(768, 28, 28, True), (768, 28, 28, True)], seed=8)
+    Zall = restated.embed(feats, 3, 1, 2048, 4096).reshape(9, 784, 4096)
+    Zq, Zb = Zall[:4], Zall[4:]
+    want = restated.per_image_min_dist(Zq, Zb)  # [4, 784, 5]
+    q = pipeline.patchset_from_Z(Zq.cuda(), precision)
+    b = pipeline.patchset_from_Z(Zb.cuda(), precision)
+    _, dmin = pipeline.min_distance_weights(q, b, "supervised", precision, return_dmin=True)
+    got = dmin.reshape(5, 4, 784).permute(1, 2, 0).cpu()
+    rel = ((got - want).abs() / want.abs().clamp_min(1e-3)).max().item()
+    assert rel <= tol, rel
+
+
+# ------------------------------------------------------------------------------- stage 3
+def test_alpha_golden(golden_dir):
+    g = gload(golden_dir, "alpha_small")
+    taus = [float(t) for t in g["taus"]]
+    for key in ("unsup", "sup"):
+        w = torch.from_numpy(g["w_" + key]).cuda()
+        a64, a32 = ops.alpha(w, taus)
+        for i, t in enumerate(taus):
+            want = g["alpha_%s_%g" % (key, t)]
+            assert np.abs(a64[i].cpu().numpy() - want).max() <= 1e-12
+            assert np.abs(a32[i].cpu().numpy() - want).max() <= 1e-7
+
+
+def test_alpha_edge_cases():
+    w = torch.tensor([[1.0, 3.0, 3.0, 2.0], [800.0, 799.0, 0.0, 0.0]]).cuda()
+    a64, _ = ops.alpha(w, [0.0, 1.0])
+    assert torch.allclose(a64[0, 0].cpu(), torch.tensor([0.0, 0.5, 0.5, 0.0], dtype=torch.float64))
+    assert torch.isfinite(a64).all()  # the reference overflows to NaN here (utils.py:253); documented divergence
+    assert abs(a64[1, 1].sum().item() - 1.0) < 1e-12
+    want = restated.alpha_from_weights(w.cpu(), 1.0, stable=True)
+    assert (a64[1].cpu() - want).abs().max().item() <= 1e-12
+
+
+def test_weighted_embed_and_pairwise_vs_oracle(golden_dir):
+    g = gload(golden_dir, "alpha_small")
+    Z = torch.from_numpy(g["Z"]).cuda()
+    for t in (0.5, 2.0):
+        a = torch.from_numpy(g["alpha_unsup_%g" % t]).float().cuda()
+        X = ops.weighted_embed(a, Z)
+        assert np.abs(X.cpu().numpy() - g["X_unsup_%g" % t]).max() <= 1e-5
+    gen = torch.Generator().manual_seed(1)
+    X = torch.randn(77, 300, generator=gen)
+    D = ops.pairwise_l2(X.cuda()).cpu().numpy()
+    want = restated.pairwise_euclidean(X.numpy())
+    assert rel_l2(D, want) <= 1e-6
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+    # odd sizes
+    X = torch.randn(5, 7, generator=gen)
+    assert rel_l2(ops.pairwise_l2(X.cuda()).cpu().numpy(), restated.pairwise_euclidean(X.numpy())) <= 1e-6
+    Z2 = torch.randn(3, 10, 6, generator=gen)
+    a2 = torch.softmax(torch.randn(3, 10, generator=gen), dim=1)
+    assert np.abs(ops.weighted_embed(a2.cuda(), Z2.cuda()).cpu().numpy() - restated.weighted_embedding(a2, Z2)).max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------- whole path
+def _check_path(res, want, labels, k, tau_idx=0):
+    Zw, ww, aw, Xw, Dw = want
+    a = res.alpha64[tau_idx].cpu()
+    assert (a - aw).abs().max().item() <= 1e-3                    # north_star: alpha max-abs <= 1e-3
+    assert rel_l2(res.X[tau_idx].cpu().numpy(), Xw) <= 1e-3       # X within 1e-3 relative L2
+    assert rel_l2(res.Dmat[tau_idx].cpu().numpy(), Dw) <= 1e-3    # distance matrix within 1e-3 relative L2
+    lab_ref = ocluster.ward_labels(Xw, k)
+    lab_gpu = ocluster.ward_labels(res.X[tau_idx].cpu().numpy().astype(np.float64), k)
+    from sklearn import metrics
+
+    assert metrics.adjusted_rand_score(lab_ref, lab_gpu) == 1.0   # identical Ward partition
+    m_ref = [metrics.normalized_mutual_info_score(labels, lab_ref), metrics.adjusted_rand_score(labels, lab_ref)]
+    m_gpu = [metrics.normalized_mutual_info_score(labels, lab_gpu), metrics.adjusted_rand_score(labels, lab_gpu)]
+    assert m_ref == m_gpu
+
+
+@pytest.mark.parametrize("precision", ["f16", "f16x3", "f32"])
+def test_full_path_unsupervised_wrn_shape(precision):
+    """BASELINE config 1 geometry at reduced image count: WRN50 layer2+layer3, 1024 -> 1024, tau = 1."""
+    n, k = 8, 4
+    feats, labels = synth.planted_features(n, [(512, 28, 28, False), (1024, 14, 14, False)], n_classes=k, seed=2023)
+    want = restated.full_path(feats, 3, 1, 1024, 1024, 1.0, "unsupervised")
+    res = pipeline.run_path([f.cuda() for f in feats], 3, 1, 1024, 1024, "unsupervised", [1.0], precision=precision)
+    assert (res.Z.cpu() - want[0]).abs().max().item() <= 2e-5
+    _check_path(res, want, labels.numpy(), k)
+
+
+def test_full_path_supervised_and_average_vit_shape():
+    """Config 3 geometry at reduced counts: ViT-B/8 tokens, 2048 -> 4096, supervised bank + average."""
+    n, nb, k = 6, 4, 3
+    layers = [(768, 28, 28, True), (768, 28, 28, True)]
+    feats, labels = synth.planted_features(n, layers, n_classes=k, seed=2023)
+    bank, _ = synth.planted_features(nb, layers, n_classes=1, seed=77)
+    want = restated.full_path(feats, 3, 1, 2048, 4096, 2.0, "supervised", bank_features=bank)
+    res = pipeline.run_path([f.cuda() for f in feats], 3, 1, 2048, 4096, "supervised", [2.0],
+                            bank_features=[f.cuda() for f in bank], precision="f16")
+    _check_path(res, want, labels.numpy(), k)
+    want_avg = restated.full_path(feats, 3, 1, 2048, 4096, 1.0, "average")
+    res_avg = pipeline.run_path([f.cuda() for f in feats], 3, 1, 2048, 4096, "average")
+    _check_path(res_avg, want_avg, labels.numpy(), k)
+
+
+def test_tau_sweep_reuses_one_distance_pass():
+    """Config 5 behaviour: every tau from one min-distance pass equals per-tau runs."""
+    feats, _ = synth.planted_features(5, [(96, 12, 12, True), (96, 12, 12, True)], seed=4)
+    f = [x.cuda() for x in feats]
+    taus = [0.5, 1.0, 2.0, 5.0, 10.0]
+    res = pipeline.run_path(f, 3, 1, 256, 512, "unsupervised", taus, precision="f16x3")
+    Z = restated.embed(feats, 3, 1, 256, 512).reshape(5, 144, 512)
+    w = restated.weight_distance_unsupervised(Z)
+    for i, t in enumerate(taus):
+        a = restated.alpha_from_weights(w, t)
+        assert (res.alpha64[i].cpu() - a).abs().max().item() <= 1e-3
+        assert rel_l2(res.X[i].cpu().numpy(), restated.weighted_embedding(a, Z)) <= 1e-3
