@@ -1,0 +1,97 @@
+"""Query-sharded multi-GPU form of the path (one process per GPU, torch.distributed / NCCL).
+
+w_i, alpha_i and X_i depend only on query image i and the read-only bank
+(reference: models/patchcore/utils.py:245-246, 265-266 -- the loop over i is independent), so:
+  rank r embeds its slice of images  ->  all-gather of the tensor-core operands (+ norms): every
+  rank holds the whole bank  ->  rank r runs stages 2/3 for its query slice  ->  all-gather of the
+  X rows  ->  Dmat.  fp32 Z never leaves its rank.  The only collectives are the two gathers.
+On CPU (gloo) the same sharding / gather logic is exercised by tests with a stand-in compute."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced slices: the first n % world ranks get one extra item."""
+    base, extra = divmod(n_items, world)
+    out, start = [], 0
+    for r in range(world):
+        cnt = base + (1 if r < extra else 0)
+        out.append((start, start + cnt))
+        start += cnt
+    return out
+
+
+def lpt_assign(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Greedy longest-processing-time assignment of work items (e.g. categories with cost
+    n_c * (n_c - 1)) to ranks; returns item indices per rank."""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    loads = [0.0] * world
+    bins: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: loads[k])
+        bins[r].append(i)
+        loads[r] += costs[i]
+    return bins
+
+
+def all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """All-gather row blocks of unequal length: local [counts[rank], ...] -> [sum(counts), ...].
+    Equal-size padded all_gather_into_tensor (one NCCL call) + compaction when counts differ."""
+    world = dist.get_world_size(group)
+    mx = max(counts)
+    tail = tuple(local.shape[1:])
+    if local.shape[0] == mx:
+        send = local.contiguous()
+    else:
+        send = torch.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
+        send[: local.shape[0]] = local
+    buf = torch.empty((world * mx,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, send, group=group)
+    if all(c == mx for c in counts):
+        return buf
+    return torch.cat([buf[r * mx : r * mx + counts[r]] for r in range(world)], dim=0)
+
+
+def run_path_sharded(
+    local_features: Sequence[torch.Tensor],
+    n_total: int,
+    patchsize: int,
+    stride: int,
+    pretrain_dim: int,
+    target_dim: int,
+    taus: Sequence[float] = (1.0,),
+    precision: str = "f16",
+    group=None,
+):
+    """Unsupervised path over n_total images sharded by shard_bounds(); `local_features` are this
+    rank's images.  Returns (alpha64_local [T,n_r,P], X_all [T,N,D], Dmat [T,N,N], w_local)."""
+    from . import ops, pipeline
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    bounds = shard_bounds(n_total, world)
+    lo_i, hi_i = bounds[rank]
+    q = pipeline.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=True)
+    assert q.n_img == hi_i - lo_i
+    P = q.P
+    row_counts = [(b - a) * P for a, b in bounds]
+    if precision == "f32":
+        bank = pipeline.PatchSet(n_total, P, q.D, q.grid, Z=all_gather_rows(q.Z, row_counts, group))
+    else:
+        bank = pipeline.PatchSet(
+            n_total, P, q.D, q.grid,
+            hi=all_gather_rows(q.hi, row_counts, group),
+            lo=None if q.lo is None else all_gather_rows(q.lo, row_counts, group),
+            n2=all_gather_rows(q.n2, row_counts, group),
+        )
+    q_self = torch.arange(lo_i, hi_i, dtype=torch.int32, device=q.Z.device)
+    w = pipeline.min_distance_weights(q, bank, "unsupervised", precision, q_self=q_self)
+    a64, a32 = ops.alpha(w, list(taus))
+    Z3 = q.Z.reshape(q.n_img, P, q.D)
+    X_loc = torch.stack([ops.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)  # [n_r, T, D]
+    X_all = all_gather_rows(X_loc, [b - a for a, b in bounds], group).permute(1, 0, 2).contiguous()  # [T, N, D]
+    Dm = torch.stack([ops.pairwise_l2(X_all[t]) for t in range(len(taus))])
+    return a64, X_all, Dm, w

@@ -20,6 +20,17 @@ import torch
 
 from . import ops
 
+# bench.py sets this to a list to collect (tag, cuda event) marks at stage boundaries
+PROFILE = None
+
+
+def _mark(tag: str) -> None:
+    if PROFILE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        PROFILE.append((tag, ev))
+
+
 _OPERAND_OF = {"f16": ("f16", False), "bf16": ("bf16", False), "f16x3": ("f16", True), "bf16x3": ("bf16", True), "f32": (None, False)}
 
 
@@ -65,6 +76,7 @@ def embed_images(
     operand, want_lo = _OPERAND_OF[precision]
     views = [ops.feature_view(f) for f in features]
     N = views[0].shape[0]
+    _mark("embed_begin")
     h, w = ops.patch_grid(views[0].shape[2], views[0].shape[3], patchsize, stride)
     P = h * w
     dev = views[0].device
@@ -83,6 +95,7 @@ def embed_images(
             want_z=need_z, operand=operand, want_lo=want_lo,
             out_z=None if Z is None else Z[sl], out_hi=None if hi is None else hi[sl], out_lo=None if lo is None else lo[sl],
         )
+    _mark("embed_end")
     ps = PatchSet(n_img=N, P=P, D=target_dim, grid=(h, w), Z=Z, hi=hi, lo=lo)
     if operand is not None:
         ps.n2 = ops.row_norms(hi, lo)
@@ -111,10 +124,12 @@ def min_distance_weights(
 ):
     """Stage 2: w [Nq, P].  mode 'unsupervised' = mean over bank images != self (utils.py:222-227),
     'supervised' = min over bank images (utils.py:230-237).  q_self[i] = bank index of query image i."""
+    _mark("mindist_begin")
     if precision == "f32":
         dmin = ops.min_dist(q.Z, None, None, bank.Z, None, None, bank.n_img, bank.P, "f32")
     else:
         dmin = ops.min_dist(q.hi, q.lo, q.n2, bank.hi, bank.lo, bank.n2, bank.n_img, bank.P, precision)
+    _mark("mindist_end")
     if mode == "unsupervised":
         if q_self is None:
             q_self = torch.arange(q.n_img, dtype=torch.int32, device=dmin.device)

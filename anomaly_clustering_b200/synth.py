@@ -62,3 +62,48 @@ CONFIGS = {
     # configs[4]: ViT-S/8 at 448x448 (3136 patches/img)
     "config5": dict(layers=[(384, 56, 56, True), (384, 56, 56, True)], n_img=64, Dp=2048, D=4096, classes=4),
 }
+
+
+def planted_features_device(
+    img_ids: Sequence[int],
+    layers: Sequence[Tuple[int, int, int, bool]],
+    n_classes: int = 4,
+    seed: int = 2023,
+    device="cuda",
+    defect_gain: float = 3.0,
+):
+    """Same construction as planted_features, generated directly on the device per GLOBAL image id
+    (so any rank can produce exactly its slice of a fixed synthetic data set).  Used by bench.py."""
+    dev = torch.device(device)
+    feats: List[torch.Tensor] = []
+    ids = list(img_ids)
+    for li, (C, H, W, tokens) in enumerate(layers):
+        g = torch.Generator(device=dev).manual_seed(seed * 1000 + li)
+        rank = 8
+        u = torch.randn(C, rank, generator=g, device=dev)
+        v = torch.randn(rank, H * W, generator=g, device=dev)
+        template = (u @ v).reshape(C, H, W) / rank ** 0.5
+        sig = torch.randn(n_classes, C, generator=g, device=dev)
+        T = (1 + H * W) if tokens else 0
+        out = torch.empty((len(ids), T, C) if tokens else (len(ids), C, H, W), dtype=torch.float32, device=dev)
+        for n, i in enumerate(ids):
+            gi = torch.Generator(device=dev).manual_seed(seed * 100003 + i * 17 + li)
+            x = template + torch.randn(C, H, W, generator=gi, device=dev)
+            c = i % n_classes
+            if c != 0:
+                gc = torch.Generator().manual_seed(seed * 7919 + i)
+                rel = torch.rand(2, generator=gc)
+                size = int(torch.randint(3, 7, (1,), generator=gc))
+                sh = max(1, size * H // 28)
+                sw = max(1, size * W // 28)
+                y0 = int(rel[0] * (H - sh))
+                x0 = int(rel[1] * (W - sw))
+                x[:, y0 : y0 + sh, x0 : x0 + sw] += defect_gain * sig[c].reshape(C, 1, 1)
+            if tokens:
+                out[n, 0] = torch.randn(C, generator=gi, device=dev)
+                out[n, 1:] = x.permute(1, 2, 0).reshape(H * W, C)
+            else:
+                out[n] = x
+        feats.append(out)
+    labels = torch.tensor([i % n_classes for i in ids])
+    return feats, labels

@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- images/s of the embedding-to-distance hot path (patchify -> alpha -> X -> dist).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one synthetic object category: hooked backbone feature
+maps resident in HBM -> Z -> w -> alpha -> X -> Dmat resident in HBM (BASELINE.json metric).
+`value` is the device-timed whole-job throughput (CUDA events, max over ranks); `e2e` repeats the
+measurement through the public API with HOST feature buffers (pinned) and host results, copies
+inside the timed region.  At N > 1 the query images are sharded over the ranks, the tensor-core
+operands are all-gathered once per step over NCCL and the X rows gathered back (strong scaling of
+the same workload).  `--impl reference` times the oracle port of the reference's torch CPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images/s (patchify→alpha→X→dist)"
+
+WORKLOADS = {
+    "config1": dict(
+        name="config1: WideResNet50 layer2+layer3 shape, 20 synthetic images x 784 patches, 1024->1024, unsupervised tau=1",
+        layers=[(512, 28, 28, False), (1024, 14, 14, False)], n_img=20, Dp=1024, D=1024, tau=1.0),
+    "config2": dict(
+        name="config2: DINO ViT-B/8 blocks.10+blocks.11 shape, 100 synthetic images x 784 patches, 2048->4096, unsupervised tau=1",
+        layers=[(768, 28, 28, True), (768, 28, 28, True)], n_img=100, Dp=2048, D=4096, tau=1.0),
+    "config4": dict(
+        name="config4 (joint bank): 1210 synthetic images x 784 patches (10 MVTec-object-sized categories), 2048->4096, unsupervised tau=1",
+        layers=[(768, 28, 28, True), (768, 28, 28, True)], n_img=1210, Dp=2048, D=4096, tau=1.0),
+    "tiny": dict(
+        name="tiny: 2x[96,12,12] tokens, 12 images x 144 patches, 256->512 (CI smoke of the bench itself)",
+        layers=[(96, 12, 12, True), (96, 12, 12, True)], n_img=12, Dp=256, D=512, tau=1.0),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_path_sample(wl, n_q, Zbank, feats_q, self_idx=None):
+    """One bounded sample of the reference's CPU path (oracle port): embed n_q images, min-distance
+    of those images against the FULL bank, alpha, X.  Cost is exactly linear in query images."""
+    import torch
+
+    from oracle import restated
+
+    t0 = time.perf_counter()
+    Zq = restated.embed(feats_q, 3, 1, wl["Dp"], wl["D"]).reshape(n_q, -1, wl["D"])
+    dm = restated.per_image_min_dist(Zq, Zbank)            # [n_q, P, n_bank]
+    if self_idx is not None:                               # unsupervised: drop the query image's own column
+        keep = torch.ones(n_q, Zbank.shape[0], dtype=torch.bool)
+        keep[torch.arange(n_q), torch.as_tensor(self_idx)] = False
+        w = torch.stack([dm[i][:, keep[i]].mean(dim=1) for i in range(n_q)])
+    else:
+        w = dm.mean(dim=2)
+    alpha = restated.alpha_from_weights(w, wl["tau"], stable=True)
+    X = restated.weighted_embedding(alpha, Zq)
+    _ = restated.pairwise_euclidean(X)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args, wl):
+    """--impl reference: the reference's own torch CPU implementation of the path (oracle port; the
+    reference is Python and cannot travel to the GPU box), all host threads, bounded sample/step."""
+    import torch
+
+    from anomaly_clustering_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_q = args.cpu_sample
+    n_bank = wl["n_img"] - 1
+    feats_q, _ = synth.planted_features(n_q, wl["layers"], seed=2023)
+    P = wl["layers"][0][1] * wl["layers"][0][2]
+    gen = torch.Generator().manual_seed(1)
+    # bank embeddings with the statistics of real ones (cdist cost does not depend on the values)
+    Zbank = torch.randn(n_bank, P, wl["D"], generator=gen) * 0.6
+    for _ in range(args.warmup):
+        cpu_path_sample(wl, n_q, Zbank, feats_q)
+    t = [cpu_path_sample(wl, n_q, Zbank, feats_q) for _ in range(args.steps)]
+    total = sum(t)
+    value = n_q * args.steps / total
+    sample = "%d query images embedded + min-distance against the full %d-image bank + alpha + X per step" % (n_q, n_bank)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps * (wl["n_img"] / n_q), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "f16x3", "bf16x3", "f32"])
+    ap.add_argument("--cpu-sample", type=int, default=2, help="query images per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+
+    import torch
+    import torch.distributed as dist
+
+    from anomaly_clustering_b200 import distributed, ops, pipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not ops.device_ok(local_rank):
+        raise SystemExit("device %d is not sm_100" % local_rank)
+    dev = torch.device("cuda", local_rank)
+    peaks = load_peaks()
+
+    n_img, layers, Dp, D, tau = wl["n_img"], wl["layers"], wl["Dp"], wl["D"], wl["tau"]
+    bounds = distributed.shard_bounds(n_img, world)
+    lo_i, hi_i = bounds[rank]
+    feats, _ = synth.planted_features_device(range(lo_i, hi_i), layers, seed=2023, device=dev)
+    P = ops.patch_grid(layers[0][1], layers[0][2], 3, 1)
+    P = P[0] * P[1]
+
+    def step(f):
+        if world == 1:
+            r = pipeline.run_path(f, 3, 1, Dp, D, "unsupervised", [tau], precision=args.precision)
+            return r.alpha32, r.X, r.Dmat
+        a64, X, Dm, _ = distributed.run_path_sharded(f, n_img, 3, 1, Dp, D, [tau], precision=args.precision)
+        return a64, X, Dm
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident timing
+    for _ in range(args.warmup):
+        step(feats)
+    sync_all()
+    pipeline.PROFILE = []
+    launches0 = ops.LAUNCHES
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    if args.cuda_profiler:
+        torch.cuda.profiler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step(feats)
+    ev1.record()
+    sync_all()
+    if args.cuda_profiler:
+        torch.cuda.profiler.stop()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.LAUNCHES - launches0
+    elapsed_ms = ev0.elapsed_time(ev1)
+    marks = pipeline.PROFILE
+    pipeline.PROFILE = None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+
+    # per-kernel time of the dominant kernel (tcgen05 min-distance), CUDA events on the launch stream
+    def span(tag):
+        b = [e for n, e in marks if n == tag + "_begin"]
+        e_ = [e for n, e in marks if n == tag + "_end"]
+        return [x.elapsed_time(y) for x, y in zip(b, e_)]
+
+    md = span("mindist")
+    md_ms = sum(md) / max(1, len(md))
+    emb = span("embed")
+    emb_ms = sum(emb) / max(1, args.steps)
+    nq_local = hi_i - lo_i
+    flops = 2.0 * (nq_local * P) * ((n_img - 1) * P) * D   # algorithmic: self pairs excluded, no padding charged
+    tflops = flops / (md_ms * 1e-3) / 1e12 if md_ms > 0 else 0.0
+    embed_bytes = nq_local * (sum(c * h * w * 4 for c, h, w, _ in layers) + P * D * 4 + (P * D * 2 if args.precision != "f32" else 0))
+    embed_gbs = embed_bytes / (emb_ms * 1e-3) / 1e9 if emb_ms > 0 else 0.0
+
+    # ---------------------------------------------------------------- end-to-end (host buffers)
+    e2e = None
+    if not args.no_e2e:
+        host = [f.cpu().pin_memory() for f in feats]
+        h2d = sum(f.numel() * 4 for f in host)
+        res_host = None
+
+        def e2e_step():
+            nonlocal res_host
+            f = [h.to(dev, non_blocking=True) for h in host]
+            a, X, Dm = step(f)
+            outs = [a, X, Dm] if rank == 0 else [a]
+            if res_host is None:
+                res_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+            for h_, o in zip(res_host, outs):
+                h_.copy_(o, non_blocking=True)
+            return sum(o.numel() * o.element_size() for o in outs)
+
+        for _ in range(3):
+            d2h = e2e_step()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            d2h = e2e_step()
+        e1.record()
+        sync_all()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        tb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        e2e = {"value": n_img * args.steps / (float(te.item()) * 1e-3), "unit": "images/s",
+               "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item())}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        n_q = min(args.cpu_sample, n_img - 1)
+        Zbank = out_Z_for_cpu(pipeline, feats, Dp, D, args.precision)   # all n_img images; self column dropped per query
+        feats_q = [f[:n_q].cpu() for f in feats]
+        cpu_path_sample(wl, 1, Zbank[: max(2, len(Zbank) // 8)], [f[:1] for f in feats_q], [0])  # warm-up
+        tcpu = cpu_path_sample(wl, n_q, Zbank, feats_q, list(range(n_q)))
+        cpu_baseline = {"value": n_q / tcpu, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": "%d query images: oracle embed + cdist/min against all %d images + alpha + X (%.1f s)"
+                                  % (n_q, len(Zbank), tcpu)}
+
+    if rank == 0:
+        value = n_img * args.steps / (elapsed_ms * 1e-3)
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    traffic = json.load(f).get("mindist_tc_dram_bytes_per_launch", {}).get(args.workload if world == 1 else "", None)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": wl["name"], "precision": args.precision, "tau": tau, "n_images": n_img, "patches_per_image": P,
+                       "embed_dim": D, "l2": "inputs larger than L2 (feature maps %.0f MB + Z %.0f MB per step)"
+                       % (sum(f.numel() * 4 for f in feats) / 1e6, nq_local * P * D * 4 / 1e6),
+                       "parallelism": "query-sharded x%d, bank all-gather (NCCL)" % world if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "mindist_tc_kernel (tcgen05, fused per-image row-min)",
+                         "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": tflops / peaks["bf16_sustained"], "peak_burst": peaks["bf16_burst"],
+                         "frac_of_burst": tflops / peaks["bf16_burst"], "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
+                         "ms_per_launch": md_ms, "algorithmic_flops_per_launch": flops, "traffic": traffic},
+            "stages": {"embed_ms_per_step": emb_ms, "embed_GBps": embed_gbs, "embed_frac_of_hbm": embed_gbs / peaks["hbm_gbs"],
+                       "mindist_ms_per_step": md_ms, "other_ms_per_step": elapsed_ms / args.steps - emb_ms - md_ms},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def out_Z_for_cpu(pipeline, feats, Dp, D, precision):
+    """Bank embeddings for the CPU baseline sample: produced once on the GPU, copied to the host
+    (inputs of the timed CPU computation, not part of it)."""
+    q = pipeline.embed_images(feats, 3, 1, Dp, D, "f32", want_z=True)
+    return q.Z.reshape(q.n_img, q.P, q.D).cpu()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,7 +147,9 @@ def test_mindist_tensor_core_kernel_arithmetic(precision, shape):
     assert rel <= (5e-4 if "x3" not in precision else 5e-5), rel
 
 
-@pytest.mark.parametrize("precision,tol", [("f16", 3e-3), ("f16x3", 2e-4), ("f32", 1e-4)])
+# f16x3 is bounded by the tensor core's fp32 accumulation over K = 3*4096 (products are exact, the
+# running sum is not re-rounded to nearest), not by operand rounding: ~0.1-0.2 absolute in d^2 ~ 1e3.
+@pytest.mark.parametrize("precision,tol", [("f16", 3e-3), ("f16x3", 1e-3), ("f32", 1e-4)])
 def test_mindist_vs_oracle_config2_width(precision, tol):
     """P = 784, D = 4096 (config-2 geometry), 4 query images vs 5 bank images (supervised form)."""
     feats, _ = synth.planted_features(9, [(768, 28, 28, True), (768, 28, 28, True)], seed=8)
