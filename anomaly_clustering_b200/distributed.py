@@ -66,15 +66,32 @@ def run_path_sharded(
     taus: Sequence[float] = (1.0,),
     precision: str = "f16",
     group=None,
+    compute=None,
 ):
     """Unsupervised path over n_total images sharded by shard_bounds(); `local_features` are this
-    rank's images.  Returns (alpha64_local [T,n_r,P], X_all [T,N,D], Dmat [T,N,N], w_local)."""
-    from . import ops, pipeline
+    rank's images.  Returns (alpha64_local [T,n_r,P], X_all [T,N,D], Dmat [T,N,N], w_local).
+
+    `compute` (tests only) substitutes the compute back-end -- an object with embed_images,
+    min_distance_weights, alpha, weighted_embed, pairwise_l2 -- so that the sharding / gather logic
+    can be exercised on CPU with gloo; the default is the CUDA library and nothing else."""
+    from . import pipeline
+
+    if compute is None:
+        from . import ops
+
+        class _Cuda:
+            embed_images = staticmethod(pipeline.embed_images)
+            min_distance_weights = staticmethod(pipeline.min_distance_weights)
+            alpha = staticmethod(ops.alpha)
+            weighted_embed = staticmethod(ops.weighted_embed)
+            pairwise_l2 = staticmethod(ops.pairwise_l2)
+
+        compute = _Cuda
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     bounds = shard_bounds(n_total, world)
     lo_i, hi_i = bounds[rank]
-    q = pipeline.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=True)
+    q = compute.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=True)
     assert q.n_img == hi_i - lo_i
     P = q.P
     row_counts = [(b - a) * P for a, b in bounds]
@@ -88,10 +105,10 @@ def run_path_sharded(
             n2=all_gather_rows(q.n2, row_counts, group),
         )
     q_self = torch.arange(lo_i, hi_i, dtype=torch.int32, device=q.Z.device)
-    w = pipeline.min_distance_weights(q, bank, "unsupervised", precision, q_self=q_self)
-    a64, a32 = ops.alpha(w, list(taus))
+    w = compute.min_distance_weights(q, bank, "unsupervised", precision, q_self=q_self)
+    a64, a32 = compute.alpha(w, list(taus))
     Z3 = q.Z.reshape(q.n_img, P, q.D)
-    X_loc = torch.stack([ops.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)  # [n_r, T, D]
+    X_loc = torch.stack([compute.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)  # [n_r, T, D]
     X_all = all_gather_rows(X_loc, [b - a for a, b in bounds], group).permute(1, 0, 2).contiguous()  # [T, N, D]
-    Dm = torch.stack([ops.pairwise_l2(X_all[t]) for t in range(len(taus))])
+    Dm = torch.stack([compute.pairwise_l2(X_all[t]) for t in range(len(taus))])
     return a64, X_all, Dm, w

@@ -1,0 +1,111 @@
+"""CPU: host-side sharding logic of the multi-GPU path, world_size 2 over gloo.  The compute
+back-end is replaced by the oracle HERE ONLY (the product default is the CUDA library); what is
+tested is shard bounds, uneven all-gather + compaction, self-exclusion with global image ids and
+the gather order of X."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from anomaly_clustering_b200 import distributed, pipeline
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_and_lpt():
+    assert distributed.shard_bounds(100, 8) == [(0, 13), (13, 26), (26, 39), (39, 52), (52, 64), (64, 76), (76, 88), (88, 100)]
+    assert distributed.shard_bounds(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    counts = [83, 150, 132, 110, 115, 167, 160, 42, 100, 151]          # MVTec object test-set sizes
+    costs = [n * (n - 1) for n in counts]
+    bins = distributed.lpt_assign(costs, 4)
+    assert sorted(i for b in bins for i in b) == list(range(10))
+    loads = [sum(costs[i] for i in b) for b in bins]
+    assert max(loads) / (sum(loads) / 4) < 1.25                           # imbalance bound quoted in SURVEY 8e
+
+
+class _OracleCompute:
+    """Stand-in compute for the CPU test (oracle arithmetic on CPU tensors)."""
+
+    @staticmethod
+    def embed_images(features, patchsize, stride, Dp, D, precision, want_z=True):
+        from oracle import restated
+
+        Z = restated.embed(features, patchsize, stride, Dp, D)
+        n = features[0].shape[0]
+        P = Z.shape[0] // n
+        return pipeline.PatchSet(n, P, D, (0, 0), Z=Z, hi=Z.clone(), lo=None, n2=(Z * Z).sum(1))
+
+    @staticmethod
+    def min_distance_weights(q, bank, mode, precision, q_self=None):
+        from oracle import restated
+
+        dm = restated.per_image_min_dist(q.Z.reshape(q.n_img, q.P, q.D), bank.hi.reshape(bank.n_img, bank.P, bank.D))
+        w = torch.empty(q.n_img, q.P)
+        for i in range(q.n_img):
+            keep = torch.ones(bank.n_img, dtype=torch.bool)
+            keep[int(q_self[i])] = False
+            w[i] = dm[i][:, keep].mean(dim=1)
+        return w
+
+    @staticmethod
+    def alpha(w, taus):
+        from oracle import restated
+
+        a = torch.stack([restated.alpha_from_weights(w, t, stable=True) for t in taus])
+        return a, a.float()
+
+    @staticmethod
+    def weighted_embed(a32, Z3):
+        return torch.bmm(a32.unsqueeze(1), Z3).squeeze(1)
+
+    @staticmethod
+    def pairwise_l2(X):
+        return torch.cdist(X.double(), X.double()).float()
+
+
+def _worker(rank, world, port, n_total, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from anomaly_clustering_b200 import synth
+
+    feats, _ = synth.planted_features(n_total, [(12, 6, 6, True), (12, 6, 6, True)], seed=3)
+    lo, hi = distributed.shard_bounds(n_total, world)[rank]
+    # uneven all-gather of row blocks
+    local = torch.arange(lo, hi, dtype=torch.float32).reshape(-1, 1).repeat(1, 3)
+    allr = distributed.all_gather_rows(local, [b - a for a, b in distributed.shard_bounds(n_total, world)])
+    assert torch.equal(allr[:, 0], torch.arange(n_total, dtype=torch.float32))
+    a64, X, Dm, w = distributed.run_path_sharded([f[lo:hi] for f in feats], n_total, 3, 1, 32, 64, [1.0, 2.0], precision="f16",
+                                                 compute=_OracleCompute)
+    np.savez(os.path.join(tmp, "r%d.npz" % rank), a=a64.numpy(), X=X.numpy(), D=Dm.numpy(), w=w.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_path_matches_single_process(tmp_path):
+    from oracle import restated
+
+    from anomaly_clustering_b200 import synth
+
+    n_total, world = 5, 2   # uneven split: 3 + 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
+    feats, _ = synth.planted_features(n_total, [(12, 6, 6, True), (12, 6, 6, True)], seed=3)
+    Z = restated.embed(feats, 3, 1, 32, 64).reshape(n_total, -1, 64)
+    w = restated.weight_distance_unsupervised(Z)
+    bounds = distributed.shard_bounds(n_total, world)
+    for r in range(world):
+        g = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
+        lo, hi = bounds[r]
+        assert np.abs(g["w"] - w[lo:hi].numpy()).max() <= 1e-5
+        for ti, tau in enumerate([1.0, 2.0]):
+            a = restated.alpha_from_weights(w, tau)
+            assert np.abs(g["a"][ti] - a[lo:hi].numpy()).max() <= 1e-6
+            X = restated.weighted_embedding(a, Z)
+            assert np.abs(g["X"][ti] - X).max() <= 1e-5           # every rank holds ALL X rows, in global order
+            assert np.abs(g["D"][ti] - restated.pairwise_euclidean(X)).max() <= 1e-4

@@ -66,6 +66,21 @@ def test_embed_config1_shape_vs_oracle():
     assert err <= 2e-5, err
 
 
+@pytest.mark.parametrize("C,Dp,D,L", [(64, 128, 128, 2), (32, 288, 288, 1), (64, 144, 288, 2), (96, 256, 256, 2), (48, 256, 512, 2),
+                                      (128, 128, 128, 1), (64, 64, 64, 2), (48, 64, 64, 1), (64, 128, 128, 1), (64, 256, 256, 1),
+                                      (64, 32, 32, 1), (64, 256, 256, 2), (48, 256, 256, 2)])
+def test_embed_periodic_fast_path_variants(C, Dp, D, L):
+    """channels_last maps take the register sliding-window kernel: every instantiated (A,B,R) period
+    pattern (9C/Dp in lowest terms, Aggregator ratio R) against the oracle."""
+    gen = torch.Generator().manual_seed(C + Dp)
+    feats = [torch.randn(2, C, 9, 13, generator=gen) for _ in range(L)]
+    want = restated.embed(feats, 3, 1, Dp, D)
+    cl = [f.cuda().contiguous(memory_format=torch.channels_last) for f in feats]
+    Z, hi, lo, _ = ops.embed(cl, 3, 1, Dp, D, operand="bf16", want_lo=True)
+    assert (Z.cpu() - want).abs().max().item() <= 1e-5
+    assert torch.equal(hi, Z.bfloat16()) and torch.equal(lo, (Z - hi.float()).bfloat16())
+
+
 def test_embed_reads_strided_views_in_place():
     """Non-contiguous inputs (channels-last maps, sliced batches) are read through their strides."""
     gen = torch.Generator().manual_seed(3)
@@ -139,7 +154,8 @@ def test_mindist_tensor_core_kernel_arithmetic(precision, shape):
     # off-diagonal (different image) entries: fp32 accumulation error only
     got = dmin.double().cpu()
     scale = want.max().item()
-    assert (got - want).abs().max().item() <= 2e-3 * scale + 1e-2  # d ~ sqrt(D); self-distances cancel to ~1e-2 at most
+    # self-distances are sqrt of a cancelled difference of two ~|x|^2 sums: ~sqrt(eps_fp32 * |x|^2 * few) ~ 5e-2
+    assert (got - want).abs().max().item() <= 2e-3 * scale + 8e-2
     mask = torch.ones_like(want, dtype=torch.bool)
     for j in range(n):
         mask[j, j * P:(j + 1) * P] = False
