@@ -501,6 +501,232 @@ __global__ void __launch_bounds__(kThreads) embed_periodic_kernel(EmbedParams p,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant of the periodic kernel (the default when the 16-byte alignment rules of
+// cp.async.bulk hold).  Same arithmetic, but the feature columns are streamed into a shared-memory
+// ring by a dedicated producer warp with 1-D bulk copies (one 3 KB token row per (ki, column) for
+// ViT-B) that run kRing columns ahead of the math, so HBM/L2 latency is hidden independently of
+// occupancy and no registers are spent on prefetch.  Consumers read each staged column once
+// (conflict-free: lane stride = channels per period), apply the LayerNorm affine in registers and
+// slide the K x K window as above.
+static constexpr int kRing = 6;
+
+__device__ __forceinline__ uint32_t e_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void e_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void e_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void e_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool e_mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void e_mbar_wait(uint32_t bar, uint32_t parity) {
+  if (e_mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!e_mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a broken pipeline must fail the launch, never hang the GPU
+  }
+}
+__device__ __forceinline__ void e_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int A, int B, int K, int R>
+__global__ void __launch_bounds__(kThreads + 32) embed_tma_kernel(EmbedParams p, int layer, int t_base, int nperiods) {
+  constexpr int CPP = A / (K * K);
+  constexpr int NOUT = B / R;
+  constexpr int NCH = kThreads * CPP;   // channels staged per column (all periods of this CTA)
+  extern __shared__ __align__(128) float ring[];          // [kRing][K][NCH]
+  __shared__ __align__(8) uint64_t s_full[kRing], s_empty[kRing];
+  __shared__ float s_mu, s_rstd;
+  const LayerDev ly = p.layers[layer];
+  const int b = p.b0 + blockIdx.z;
+  const int y = blockIdx.y / p.nxseg, xseg = blockIdx.y - y * p.nxseg;
+  const int xa = xseg * p.xseg_len, xb = min(p.w0, xa + p.xseg_len);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.x * kThreads;
+  const int c_start = m0 * CPP;
+  const int nch = min(NCH, ly.C - c_start);               // multiple of 4 (host guarantees C % 4 == 0)
+  const int ncols = (xb - xa) + K - 1;                     // staged input columns xa-pad .. xb-1-pad+K-1
+  if (tid == 0) {
+    for (int i = 0; i < kRing; ++i) {
+      e_mbar_init(e_smem_u32(&s_full[i]), 1);
+      e_mbar_init(e_smem_u32(&s_empty[i]), kThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    float mu = 0.f, rstd = 1.f;
+    if (p.layernorm) {
+      const double* st = p.stats + (((long long)b * p.L + layer) * kStatSplit) * 2;
+      double a = 0, q = 0;
+      for (int i = lane; i < kStatSplit; i += 32) { a += st[2 * i]; q += st[2 * i + 1]; }
+      a = warp_sum(a);
+      q = warp_sum(q);
+      const double n = (double)ly.C * ly.H * ly.W;
+      const double m = a / n;
+      double var = q / n - m * m;
+      if (var < 0) var = 0;
+      mu = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+    if (lane == 0) { s_mu = mu; s_rstd = rstd; }
+  }
+  __syncthreads();
+
+  bool rowok[K];
+#pragma unroll
+  for (int ki = 0; ki < K; ++ki) {
+    const int iy = y - p.pad + ki;
+    rowok[ki] = (iy >= 0) && (iy < ly.H);
+  }
+
+  if (warp == kThreads / 32) {
+    // ================================================================ producer warp
+    if (lane == 0) {
+      const float* src = ly.ptr + (long long)b * ly.sb + c_start;
+      const uint32_t bytes_row = (uint32_t)nch * 4u;
+      for (int j = 0; j < ncols; ++j) {
+        const int slot = j % kRing;
+        const uint32_t ph = (uint32_t)(j / kRing) & 1u;
+        e_mbar_wait(e_smem_u32(&s_empty[slot]), ph ^ 1u);
+        const int ix = xa - p.pad + j;
+        const bool cin = (ix >= 0) && (ix < ly.W);
+        uint32_t nrows = 0;
+#pragma unroll
+        for (int ki = 0; ki < K; ++ki) nrows += (cin && rowok[ki]) ? 1u : 0u;
+        const uint32_t fb = e_smem_u32(&s_full[slot]);
+        if (nrows == 0) {
+          e_mbar_arrive(fb);
+        } else {
+          e_mbar_expect_tx(fb, nrows * bytes_row);
+#pragma unroll
+          for (int ki = 0; ki < K; ++ki)
+            if (cin && rowok[ki])
+              e_bulk_g2s(e_smem_u32(ring + ((size_t)slot * K + ki) * NCH),
+                         src + (long long)(y - p.pad + ki) * ly.sh + (long long)ix * ly.sw, bytes_row, fb);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================================================== consumers (kThreads)
+  const float mu = s_mu, rstd = s_rstd;
+  const int m = m0 + tid;
+  const bool active = m < nperiods;
+  float v[CPP][K][K];
+#pragma unroll
+  for (int c = 0; c < CPP; ++c)
+#pragma unroll
+    for (int ki = 0; ki < K; ++ki)
+#pragma unroll
+      for (int kj = 0; kj < K; ++kj) v[c][ki][kj] = 0.f;
+  const long long row0 = ((long long)b * p.h0 + y) * p.w0;
+  const int t0 = t_base + m * NOUT;
+
+  for (int j = 0; j < ncols; ++j) {
+    const int slot = j % kRing;
+    const uint32_t ph = (uint32_t)(j / kRing) & 1u;
+    const int ix = xa - p.pad + j;
+    const bool cin = (ix >= 0) && (ix < ly.W);
+    // slide the window left and append staged column j
+    e_mbar_wait(e_smem_u32(&s_full[slot]), ph);
+    const float* col = ring + (size_t)slot * K * NCH + tid * CPP;
+#pragma unroll
+    for (int c = 0; c < CPP; ++c)
+#pragma unroll
+      for (int ki = 0; ki < K; ++ki) {
+#pragma unroll
+        for (int kj = 0; kj + 1 < K; ++kj) v[c][ki][kj] = v[c][ki][kj + 1];
+        const bool ok = cin && rowok[ki] && active;
+        v[c][ki][K - 1] = ok ? (col[ki * NCH + c] - mu) * rstd : 0.f;
+      }
+    __syncwarp();
+    if (lane == 0) e_mbar_arrive(e_smem_u32(&s_empty[slot]));
+    const int x = xa + j - (K - 1);     // position whose window is now complete
+    if (x < xa || !active) continue;
+    float out[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+      float acc_o = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) {
+        const int r = o * R + jj;
+        const int f0 = (r * A) / B, f1 = ((r + 1) * A + B - 1) / B;
+        float sacc = 0.f;
+#pragma unroll
+        for (int f = 0; f < A; ++f)
+          if (f >= f0 && f < f1) sacc += v[f / (K * K)][(f % (K * K)) / K][f % K];
+        acc_o += sacc * (1.0f / (float)(f1 - f0));
+      }
+      out[o] = (R == 1) ? acc_o : acc_o * (1.0f / (float)R);
+    }
+    const long long idx = (row0 + x) * p.ldz + t0;
+    if (p.Z) {
+      if (NOUT % 4 == 0 && ((p.ldz | t_base) & 3) == 0) {
+#pragma unroll
+        for (int o = 0; o < NOUT; o += 4) *reinterpret_cast<float4*>(p.Z + idx + o) = make_float4(out[o], out[o + 1], out[o + 2], out[o + 3]);
+      } else {
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) p.Z[idx + o] = out[o];
+      }
+    }
+    if (p.Zhi) {
+      if (p.op_dtype == AC_DT_F16) {
+        __align__(16) __half h[NOUT];
+        __align__(16) __half l[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) { h[o] = __float2half_rn(out[o]); l[o] = __float2half_rn(out[o] - __half2float(h[o])); }
+        __half* ph_ = reinterpret_cast<__half*>(p.Zhi) + idx;
+        __half* pl_ = p.Zlo ? reinterpret_cast<__half*>(p.Zlo) + idx : nullptr;
+        if (NOUT % 8 == 0 && ((p.ldz | t_base) & 7) == 0) {
+#pragma unroll
+          for (int o = 0; o < NOUT; o += 8) {
+            *reinterpret_cast<uint4*>(ph_ + o) = *reinterpret_cast<const uint4*>(&h[o]);
+            if (pl_) *reinterpret_cast<uint4*>(pl_ + o) = *reinterpret_cast<const uint4*>(&l[o]);
+          }
+        } else {
+#pragma unroll
+          for (int o = 0; o < NOUT; ++o) { ph_[o] = h[o]; if (pl_) pl_[o] = l[o]; }
+        }
+      } else {
+        __align__(16) __nv_bfloat16 h[NOUT];
+        __align__(16) __nv_bfloat16 l[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) { h[o] = __float2bfloat16_rn(out[o]); l[o] = __float2bfloat16_rn(out[o] - __bfloat162float(h[o])); }
+        __nv_bfloat16* ph_ = reinterpret_cast<__nv_bfloat16*>(p.Zhi) + idx;
+        __nv_bfloat16* pl_ = p.Zlo ? reinterpret_cast<__nv_bfloat16*>(p.Zlo) + idx : nullptr;
+        if (NOUT % 8 == 0 && ((p.ldz | t_base) & 7) == 0) {
+#pragma unroll
+          for (int o = 0; o < NOUT; o += 8) {
+            *reinterpret_cast<uint4*>(ph_ + o) = *reinterpret_cast<const uint4*>(&h[o]);
+            if (pl_) *reinterpret_cast<uint4*>(pl_ + o) = *reinterpret_cast<const uint4*>(&l[o]);
+          }
+        } else {
+#pragma unroll
+          for (int o = 0; o < NOUT; ++o) { ph_[o] = h[o]; if (pl_) pl_[o] = l[o]; }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // standalone compat kernels
 __global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int H, int W, int k, int s, int pad,
@@ -782,6 +1008,15 @@ static bool periodic_instantiated(const Periodic& pr) {
   return false;
 }
 
+static int g_embed_variant = 0;   // test hook (ac_debug_set key 2): 0 = auto, 1 = force LDG periodic, 2 = force generic tap kernel
+
+static bool tma_aligned(const EmbedParams& p, int l) {
+  const LayerDev& ly = p.layers[l];
+  if (ly.C % 4 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(ly.ptr) & 15) != 0) return false;
+  return (ly.sb % 4 == 0) && (ly.sh % 4 == 0) && (ly.sw % 4 == 0);
+}
+
 static int launch_periodic(EmbedParams p, const Periodic& pr, int l, int num_sms, cudaStream_t st) {
   // split rows into x segments until the launch has a few waves of CTAs
   const int gx = ceil_div(pr.nperiods, kThreads);
@@ -790,11 +1025,19 @@ static int launch_periodic(EmbedParams p, const Periodic& pr, int l, int num_sms
   p.xseg_len = ceil_div(p.w0, nxseg);
   p.nxseg = ceil_div(p.w0, p.xseg_len);
   dim3 grid(gx, p.h0 * p.nxseg, p.B);
-#define X(a, b, r)                                                                              \
-  if (pr.A == a && pr.B == b && pr.R == r) {                                                    \
-    embed_periodic_kernel<a, b, 3, r><<<grid, kThreads, 0, st>>>(p, l, pr.t_base, pr.nperiods); \
-    AC_LAUNCH_CHECK();                                                                          \
-    return AC_OK;                                                                               \
+  const bool use_tma = (g_embed_variant == 0) && tma_aligned(p, l);
+#define X(a, b, r)                                                                                         \
+  if (pr.A == a && pr.B == b && pr.R == r) {                                                               \
+    if (use_tma) {                                                                                         \
+      auto kern = embed_tma_kernel<a, b, 3, r>;                                                            \
+      const size_t smem = (size_t)kRing * 3 * kThreads * (a / 9) * sizeof(float);                          \
+      AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      kern<<<grid, kThreads + 32, smem, st>>>(p, l, pr.t_base, pr.nperiods);                               \
+    } else {                                                                                               \
+      embed_periodic_kernel<a, b, 3, r><<<grid, kThreads, 0, st>>>(p, l, pr.t_base, pr.nperiods);          \
+    }                                                                                                      \
+    AC_LAUNCH_CHECK();                                                                                     \
+    return AC_OK;                                                                                          \
   }
   AC_PERIODIC_CASES(X)
 #undef X
@@ -898,7 +1141,7 @@ extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, i
   bool need_chunks = false;
   for (int l = 0; l < L; ++l) {
     pr[l] = periodic_of(plan, l);
-    if (pr[l].ok && !periodic_instantiated(pr[l])) pr[l].ok = 0;
+    if (pr[l].ok && (!periodic_instantiated(pr[l]) || g_embed_variant == 2)) pr[l].ok = 0;
     if (!pr[l].ok && plan.pl[l].nchunks > 0) need_chunks = true;
   }
   if (need_chunks)
@@ -948,6 +1191,12 @@ extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, i
       if (rc) return rc;
     }
   }
+  return AC_OK;
+}
+
+extern "C" int ac_debug_set_embed(int value) {
+  if (value < 0 || value > 2) return AC_ERR_INVALID;
+  g_embed_variant = value;
   return AC_OK;
 }
 

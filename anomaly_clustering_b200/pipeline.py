@@ -69,10 +69,11 @@ def embed_images(
     precision: str = "f16",
     want_z: bool = True,
     layernorm: bool = True,
-    batch: int = 16,
+    batch: Optional[int] = None,
 ) -> PatchSet:
-    """Stage 1 for a set of images, `batch` images per launch so that the LayerNorm statistics pass
-    and the fused embed kernel both find the feature maps in L2."""
+    """Stage 1 for a set of images in one C-ABI call (the library itself walks the images in
+    L2-sized sub-batches so the LayerNorm statistics pass and the fused embed kernel share the
+    feature maps in L2); `batch` only caps the images per call."""
     operand, want_lo = _OPERAND_OF[precision]
     views = [ops.feature_view(f) for f in features]
     N = views[0].shape[0]
@@ -87,8 +88,9 @@ def embed_images(
         tdt = torch.float16 if operand == "f16" else torch.bfloat16
         hi = torch.empty(N * P, target_dim, dtype=tdt, device=dev)
         lo = torch.empty(N * P, target_dim, dtype=tdt, device=dev) if want_lo else None
-    for b0 in range(0, N, batch):
-        b1 = min(N, b0 + batch)
+    step = N if not batch else batch
+    for b0 in range(0, N, step):
+        b1 = min(N, b0 + step)
         sl = slice(b0 * P, b1 * P)
         ops.embed(
             [v[b0:b1] for v in views], patchsize, stride, pretrain_dim, target_dim, layernorm=layernorm,

@@ -81,6 +81,26 @@ def test_embed_periodic_fast_path_variants(C, Dp, D, L):
     assert torch.equal(hi, Z.bfloat16()) and torch.equal(lo, (Z - hi.float()).bfloat16())
 
 
+def test_embed_kernel_variants_agree():
+    """TMA-staged, LDG-periodic and generic tap kernels compute the same Z (config-2 geometry)."""
+    from anomaly_clustering_b200 import _lib
+
+    lib = _lib.load()
+    feats, _ = synth.planted_features(2, [(768, 28, 28, True), (768, 28, 28, True)], seed=9)
+    f = [x.cuda() for x in feats]
+    outs = []
+    try:
+        for variant in (0, 1, 2):
+            assert lib.ac_debug_set(2, variant) == 0
+            Z, hi, _, _ = ops.embed(f, 3, 1, 2048, 4096, operand="f16")
+            outs.append((Z.clone(), hi.clone()))
+    finally:
+        lib.ac_debug_set(2, 0)
+    assert torch.equal(outs[0][0], outs[1][0])                      # same arithmetic order
+    assert (outs[0][0] - outs[2][0]).abs().max().item() <= 2e-6     # generic kernel: FMA with weights
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
 def test_embed_reads_strided_views_in_place():
     """Non-contiguous inputs (channels-last maps, sliced batches) are read through their strides."""
     gen = torch.Generator().manual_seed(3)
