@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstring>
 #include <memory>
+#include <type_traits>
 #include <mutex>
 
 namespace ac {
@@ -116,7 +117,20 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(EmbedParams p, double* st
   float s = 0.f, q = 0.f;
   const bool tok = (ly.sc == 1 && ly.sw == ly.C && ly.sh == (long long)ly.W * ly.C);
   const bool cnn = (ly.sw == 1 && ly.sh == ly.W && ly.sc == (long long)ly.H * ly.W);
-  if (tok || cnn) {
+  if ((tok || cnn) && (n % (4LL * gridDim.x) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+    // dense image, 16-byte aligned slices: 128-bit loads, 4 independent accumulator pairs
+    const float4* b4 = reinterpret_cast<const float4*>(base);
+    float s2 = 0.f, q2 = 0.f, s3 = 0.f, q3 = 0.f, s4 = 0.f, q4 = 0.f;
+    for (long long e = lo_e / 4 + threadIdx.x; e < hi_e / 4; e += blockDim.x) {
+      const float4 v = __ldg(b4 + e);
+      s += v.x; q = fmaf(v.x, v.x, q);
+      s2 += v.y; q2 = fmaf(v.y, v.y, q2);
+      s3 += v.z; q3 = fmaf(v.z, v.z, q3);
+      s4 += v.w; q4 = fmaf(v.w, v.w, q4);
+    }
+    s = (s + s2) + (s3 + s4);
+    q = (q + q2) + (q3 + q4);
+  } else if (tok || cnn) {
     for (long long e = lo_e + threadIdx.x; e < hi_e; e += blockDim.x) {
       const float v = __ldg(base + e);
       s += v;
@@ -547,7 +561,7 @@ __device__ __forceinline__ void e_bulk_g2s(uint32_t dst, const void* src, uint32
 }
 
 template <int A, int B, int K, int R>
-__global__ void __launch_bounds__(kThreads + 32) embed_tma_kernel(EmbedParams p, int layer, int t_base, int nperiods) {
+__global__ void __launch_bounds__(kThreads + 32, 3) embed_tma_kernel(EmbedParams p, int layer, int t_base, int nperiods) {
   constexpr int CPP = A / (K * K);
   constexpr int NOUT = B / R;
   constexpr int NCH = kThreads * CPP;   // channels staged per column (all periods of this CTA)
@@ -627,10 +641,26 @@ __global__ void __launch_bounds__(kThreads + 32) embed_tma_kernel(EmbedParams p,
   }
 
   // ================================================================== consumers (kThreads)
+  static_assert(K == 3, "the rotating register window below is unrolled for 3x3 patches");
   const float mu = s_mu, rstd = s_rstd;
   const int m = m0 + tid;
   const bool active = m < nperiods;
-  float v[CPP][K][K];
+  // LayerNorm affine folded into one FFMA per value; rows outside the map get scale = offset = 0
+  // and read a valid staged row instead (finite * 0), so no per-value select is needed
+  float sc[K], of[K];
+  int krow[K];
+  int kvalid = 0;
+#pragma unroll
+  for (int ki = 0; ki < K; ++ki)
+    if (rowok[ki]) kvalid = ki;
+#pragma unroll
+  for (int ki = 0; ki < K; ++ki) {
+    const bool ok = rowok[ki] && active;
+    sc[ki] = ok ? rstd : 0.f;
+    of[ki] = ok ? -mu * rstd : 0.f;
+    krow[ki] = (rowok[ki] ? ki : kvalid) * NCH;
+  }
+  float v[CPP][K][K];   // [channel][ki][physical column slot]
 #pragma unroll
   for (int c = 0; c < CPP; ++c)
 #pragma unroll
@@ -638,29 +668,34 @@ __global__ void __launch_bounds__(kThreads + 32) embed_tma_kernel(EmbedParams p,
 #pragma unroll
       for (int kj = 0; kj < K; ++kj) v[c][ki][kj] = 0.f;
   const long long row0 = ((long long)b * p.h0 + y) * p.w0;
-  const int t0 = t_base + m * NOUT;
+  const int t0 = t_base + (active ? m : 0) * NOUT;
 
-  for (int j = 0; j < ncols; ++j) {
+  // one step: append staged column j into physical slot j % K, then emit position xa + j - (K-1);
+  // ROT = (j + 1) % K maps logical kj -> physical (kj + ROT) % K, all indices compile-time
+  auto step = [&](auto rot_tag, int j) {
+    constexpr int ROT = decltype(rot_tag)::value;
+    constexpr int SLOT = (ROT + K - 1) % K;
     const int slot = j % kRing;
     const uint32_t ph = (uint32_t)(j / kRing) & 1u;
     const int ix = xa - p.pad + j;
     const bool cin = (ix >= 0) && (ix < ly.W);
-    // slide the window left and append staged column j
     e_mbar_wait(e_smem_u32(&s_full[slot]), ph);
-    const float* col = ring + (size_t)slot * K * NCH + tid * CPP;
+    if (cin) {
+      const float* col = ring + (size_t)slot * K * NCH + tid * CPP;
 #pragma unroll
-    for (int c = 0; c < CPP; ++c)
+      for (int c = 0; c < CPP; ++c)
 #pragma unroll
-      for (int ki = 0; ki < K; ++ki) {
+        for (int ki = 0; ki < K; ++ki) v[c][ki][SLOT] = fmaf(col[krow[ki] + c], sc[ki], of[ki]);
+    } else {
 #pragma unroll
-        for (int kj = 0; kj + 1 < K; ++kj) v[c][ki][kj] = v[c][ki][kj + 1];
-        const bool ok = cin && rowok[ki] && active;
-        v[c][ki][K - 1] = ok ? (col[ki * NCH + c] - mu) * rstd : 0.f;
-      }
+      for (int c = 0; c < CPP; ++c)
+#pragma unroll
+        for (int ki = 0; ki < K; ++ki) v[c][ki][SLOT] = 0.f;
+    }
     __syncwarp();
     if (lane == 0) e_mbar_arrive(e_smem_u32(&s_empty[slot]));
-    const int x = xa + j - (K - 1);     // position whose window is now complete
-    if (x < xa || !active) continue;
+    const int x = xa + j - (K - 1);
+    if (x < xa || !active) return;
     float out[NOUT];
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) {
@@ -672,7 +707,7 @@ __global__ void __launch_bounds__(kThreads + 32) embed_tma_kernel(EmbedParams p,
         float sacc = 0.f;
 #pragma unroll
         for (int f = 0; f < A; ++f)
-          if (f >= f0 && f < f1) sacc += v[f / (K * K)][(f % (K * K)) / K][f % K];
+          if (f >= f0 && f < f1) sacc += v[f / (K * K)][(f % (K * K)) / K][((f % K) + ROT) % K];
         acc_o += sacc * (1.0f / (float)(f1 - f0));
       }
       out[o] = (R == 1) ? acc_o : acc_o * (1.0f / (float)R);
@@ -690,40 +725,63 @@ __global__ void __launch_bounds__(kThreads + 32) embed_tma_kernel(EmbedParams p,
     if (p.Zhi) {
       if (p.op_dtype == AC_DT_F16) {
         __align__(16) __half h[NOUT];
-        __align__(16) __half l[NOUT];
 #pragma unroll
-        for (int o = 0; o < NOUT; ++o) { h[o] = __float2half_rn(out[o]); l[o] = __float2half_rn(out[o] - __half2float(h[o])); }
+        for (int o = 0; o < NOUT; ++o) h[o] = __float2half_rn(out[o]);
         __half* ph_ = reinterpret_cast<__half*>(p.Zhi) + idx;
-        __half* pl_ = p.Zlo ? reinterpret_cast<__half*>(p.Zlo) + idx : nullptr;
-        if (NOUT % 8 == 0 && ((p.ldz | t_base) & 7) == 0) {
+        const bool vec = (NOUT % 8 == 0) && (((p.ldz | t_base) & 7) == 0);
+        if (vec) {
 #pragma unroll
-          for (int o = 0; o < NOUT; o += 8) {
-            *reinterpret_cast<uint4*>(ph_ + o) = *reinterpret_cast<const uint4*>(&h[o]);
-            if (pl_) *reinterpret_cast<uint4*>(pl_ + o) = *reinterpret_cast<const uint4*>(&l[o]);
-          }
+          for (int o = 0; o < NOUT; o += 8) *reinterpret_cast<uint4*>(ph_ + o) = *reinterpret_cast<const uint4*>(&h[o]);
         } else {
 #pragma unroll
-          for (int o = 0; o < NOUT; ++o) { ph_[o] = h[o]; if (pl_) pl_[o] = l[o]; }
+          for (int o = 0; o < NOUT; ++o) ph_[o] = h[o];
+        }
+        if (p.Zlo) {
+          __align__(16) __half l[NOUT];
+#pragma unroll
+          for (int o = 0; o < NOUT; ++o) l[o] = __float2half_rn(out[o] - __half2float(h[o]));
+          __half* pl_ = reinterpret_cast<__half*>(p.Zlo) + idx;
+          if (vec) {
+#pragma unroll
+            for (int o = 0; o < NOUT; o += 8) *reinterpret_cast<uint4*>(pl_ + o) = *reinterpret_cast<const uint4*>(&l[o]);
+          } else {
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) pl_[o] = l[o];
+          }
         }
       } else {
         __align__(16) __nv_bfloat16 h[NOUT];
-        __align__(16) __nv_bfloat16 l[NOUT];
 #pragma unroll
-        for (int o = 0; o < NOUT; ++o) { h[o] = __float2bfloat16_rn(out[o]); l[o] = __float2bfloat16_rn(out[o] - __bfloat162float(h[o])); }
+        for (int o = 0; o < NOUT; ++o) h[o] = __float2bfloat16_rn(out[o]);
         __nv_bfloat16* ph_ = reinterpret_cast<__nv_bfloat16*>(p.Zhi) + idx;
-        __nv_bfloat16* pl_ = p.Zlo ? reinterpret_cast<__nv_bfloat16*>(p.Zlo) + idx : nullptr;
-        if (NOUT % 8 == 0 && ((p.ldz | t_base) & 7) == 0) {
+        const bool vec = (NOUT % 8 == 0) && (((p.ldz | t_base) & 7) == 0);
+        if (vec) {
 #pragma unroll
-          for (int o = 0; o < NOUT; o += 8) {
-            *reinterpret_cast<uint4*>(ph_ + o) = *reinterpret_cast<const uint4*>(&h[o]);
-            if (pl_) *reinterpret_cast<uint4*>(pl_ + o) = *reinterpret_cast<const uint4*>(&l[o]);
-          }
+          for (int o = 0; o < NOUT; o += 8) *reinterpret_cast<uint4*>(ph_ + o) = *reinterpret_cast<const uint4*>(&h[o]);
         } else {
 #pragma unroll
-          for (int o = 0; o < NOUT; ++o) { ph_[o] = h[o]; if (pl_) pl_[o] = l[o]; }
+          for (int o = 0; o < NOUT; ++o) ph_[o] = h[o];
+        }
+        if (p.Zlo) {
+          __align__(16) __nv_bfloat16 l[NOUT];
+#pragma unroll
+          for (int o = 0; o < NOUT; ++o) l[o] = __float2bfloat16_rn(out[o] - __bfloat162float(h[o]));
+          __nv_bfloat16* pl_ = reinterpret_cast<__nv_bfloat16*>(p.Zlo) + idx;
+          if (vec) {
+#pragma unroll
+            for (int o = 0; o < NOUT; o += 8) *reinterpret_cast<uint4*>(pl_ + o) = *reinterpret_cast<const uint4*>(&l[o]);
+          } else {
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) pl_[o] = l[o];
+          }
         }
       }
     }
+  };
+  for (int j0 = 0; j0 < ncols; j0 += 3) {
+    step(std::integral_constant<int, 1>{}, j0);
+    if (j0 + 1 < ncols) step(std::integral_constant<int, 2>{}, j0 + 1);
+    if (j0 + 2 < ncols) step(std::integral_constant<int, 0>{}, j0 + 2);
   }
 }
 

@@ -406,7 +406,7 @@ static uint32_t make_idesc(int M, int N, bool bf16) {
 }
 
 static int g_tc_cta_group = 2;   // test hook (ac_debug_set): 1 = single-CTA MMAs, 2 = CTA pairs
-static int g_tc_gm = 8;
+static int g_tc_gm = 16;  // query blocks per raster group: 16 x 2 MB of A + the streaming bank images stay L2-resident (tuned on B200)
 
 template <int G, int kStages>
 static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {

@@ -31,7 +31,7 @@ def run(reps):
     return e0.elapsed_time(e1) / reps
 
 
-for key, vals in ((1, [1, 2, 4, 8, 16, 32, 64]),):
+for key, vals in ((1, [10, 12, 14, 16, 18, 20, 24]),):
     for v in vals:
         lib.ac_debug_set(key, v)
         run(2)

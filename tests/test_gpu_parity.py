@@ -96,9 +96,9 @@ def test_embed_kernel_variants_agree():
             outs.append((Z.clone(), hi.clone()))
     finally:
         lib.ac_debug_set(2, 0)
-    assert torch.equal(outs[0][0], outs[1][0])                      # same arithmetic order
+    assert (outs[0][0] - outs[1][0]).abs().max().item() <= 2e-6     # LN affine as one FFMA vs (v-mu)*rstd
     assert (outs[0][0] - outs[2][0]).abs().max().item() <= 2e-6     # generic kernel: FMA with weights
-    assert torch.equal(outs[0][1], outs[1][1])
+    assert (outs[0][1].float() - outs[1][1].float()).abs().max().item() <= 4e-3
 
 
 def test_embed_reads_strided_views_in_place():
