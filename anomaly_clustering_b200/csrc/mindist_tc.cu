@@ -49,7 +49,23 @@ struct __align__(64) TcParams {
   int nt, wmain, wlast;      // tiles per bank image, widths (multiples of 16)
   int n_mblocks, GM;
   uint32_t idesc_main, idesc_last;
+  // symmetric (self-bank) mode: every unordered image pair is multiplied once
+  int sym;                   // 0 = every (query block, bank image) unit; 1 = only pairs owned by the query image
+  int q_img0;                // global image index of query row 0 (query slice of a sharded run)
+  int KU;                    // units per query block in sym mode
+  unsigned int* colmin;      // [nq_img, nb_img*P] squared distances (fp32 bits), atomicMin target
 };
+
+// Ownership of the unordered pair {i, j} of N images: the image that sees the other one within the
+// next floor((N-1)/2) positions of the circular order (ties at N/2 go to the smaller index).
+__host__ __device__ inline bool pair_owned(int i, int j, int N) {
+  int d = j - i;
+  if (d < 0) d += N;
+  if (d == 0) return false;
+  if (2 * d < N) return true;
+  if (2 * d == N) return i < j;
+  return false;
+}
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -194,13 +210,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-__device__ __forceinline__ void decode_unit(const TcParams& p, long long u, int& mb, int& img) {
-  const long long per_group = (long long)p.GM * p.nb_img;
+// unit index -> (query block, bank image); false when the unit carries no work (sym mode: no row of
+// the block owns the pair).  Every warp role evaluates this identically, so skipped units touch no barrier.
+template <int G>
+__device__ __forceinline__ bool decode_unit(const TcParams& p, long long u, int& mb, int& img) {
+  const int per_mb = p.sym ? p.KU : p.nb_img;
+  const long long per_group = (long long)p.GM * per_mb;
   const int mg = (int)(u / per_group);
   const long long rem = u - (long long)mg * per_group;
   const int gm_cur = min(p.GM, p.n_mblocks - mg * p.GM);
-  img = (int)(rem / gm_cur);
-  mb = mg * p.GM + (int)(rem - (long long)img * gm_cur);
+  const int k = (int)(rem / gm_cur);
+  mb = mg * p.GM + (int)(rem - (long long)k * gm_cur);
+  if (!p.sym) { img = k; return true; }
+  const long long r0 = (long long)mb * (kTileM * G);
+  const long long r1 = min(p.Mq, r0 + kTileM * G) - 1;
+  const int i0 = p.q_img0 + (int)(r0 / p.P), i1 = p.q_img0 + (int)(r1 / p.P);
+  img = (i0 + 1 + k) % p.nb_img;
+  for (int i = i0; i <= i1; ++i)
+    if (pair_owned(i, img, p.nb_img)) return true;
+  return false;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -255,7 +283,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
       const uint32_t full0 = (G == 2) ? mapa_rank(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
       for (long long u = worker; u < p.total_units; u += nworkers) {
         int mb, img;
-        decode_unit(p, u, mb, img);
+        if (!decode_unit<G>(p, u, mb, img)) continue;
         const int arow = mb * (kTileM * G) + (int)rank * kTileM;
         for (int t = 0; t < p.nt; ++t) {
           const bool last = (t == p.nt - 1);
@@ -284,6 +312,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
       uint32_t stage = 0, phase = 0;
       uint32_t tile_ctr = 0;
       for (long long u = worker; u < p.total_units; u += nworkers) {
+        int mb_, img_;
+        if (!decode_unit<G>(p, u, mb_, img_)) continue;
         for (int t = 0; t < p.nt; ++t, ++tile_ctr) {
           const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
           const uint32_t idesc = (t == p.nt - 1) ? p.idesc_last : p.idesc_main;
@@ -318,8 +348,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
     uint32_t tile_ctr = 0;
     for (long long u = worker; u < p.total_units; u += nworkers) {
       int mb, img;
-      decode_unit(p, u, mb, img);
+      if (!decode_unit<G>(p, u, mb, img)) continue;
       const long long row = (long long)mb * (kTileM * G) + rank * kTileM + et;
+      const bool rvalid = row < p.Mq;
+      // sym mode: this row contributes (row-min and column-min) only if its image owns the pair
+      const int irow = p.q_img0 + (int)((rvalid ? row : p.Mq - 1) / p.P);
+      const bool act = rvalid && (!p.sym || pair_owned(irow, img, p.nb_img));
+      const float qn = rvalid ? __ldg(p.qn2 + row) : 0.f;
+      // images covered by this warp's 32 consecutive rows (at most two when P >= 32)
+      const long long wrow0 = row - lane;
+      const int ilo = p.q_img0 + (int)(min(wrow0, p.Mq - 1) / p.P);
+      const int ihi = p.q_img0 + (int)(min(wrow0 + 31, p.Mq - 1) / p.P);
       float best = INFINITY;
       for (int t = 0; t < p.nt; ++t, ++tile_ctr) {
         const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
@@ -338,11 +377,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
           AC_TMEM_LD16(taddr + c0, v0);
           if (two) AC_TMEM_LD16(taddr + c0 + 16, v1);
           tmem_ld_wait();
+          if (!p.sym) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) best = fminf(best, fmaf(-2.f, __uint_as_float(v0[i]), bn[c0 + i]));
-          if (two) {
+            for (int i = 0; i < 16; ++i) best = fminf(best, fmaf(-2.f, __uint_as_float(v0[i]), bn[c0 + i]));
+            if (two) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) best = fminf(best, fmaf(-2.f, __uint_as_float(v1[i]), bn[c0 + 16 + i]));
+              for (int i = 0; i < 16; ++i) best = fminf(best, fmaf(-2.f, __uint_as_float(v1[i]), bn[c0 + 16 + i]));
+            }
+          } else {
+            // row-min as above + column-min over the rows of this warp: non-negative floats order like
+            // their bit patterns, so one REDUX.MIN.U32 per column does the 32-row reduction; lane i keeps
+            // column c0+i and the warp issues one coalesced atomicMin per 32 columns
+            unsigned int keep_lo = 0x7f800000u, keep_hi = 0x7f800000u;
+            const bool in_lo = act && (irow == ilo), in_hi = act && (irow == ihi) && (ihi != ilo);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !two) break;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float part = fmaf(-2.f, __uint_as_float(h ? v1[i] : v0[i]), bn[c0 + h * 16 + i]);
+                best = fminf(best, part);
+                const unsigned int e = __float_as_uint(fmaxf(part + qn, 0.f));
+                const unsigned int m_lo = __reduce_min_sync(0xffffffffu, in_lo ? e : 0x7f800000u);
+                if (lane == h * 16 + i) keep_lo = m_lo;
+                if (ihi != ilo) {   // warp-uniform: the warp straddles two query images
+                  const unsigned int m_hi = __reduce_min_sync(0xffffffffu, in_hi ? e : 0x7f800000u);
+                  if (lane == h * 16 + i) keep_hi = m_hi;
+                }
+              }
+            }
+            const int c = c0 + lane;
+            if (c < valid) {
+              if (keep_lo != 0x7f800000u) atomicMin(p.colmin + (long long)(ilo - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, keep_lo);
+              if (ihi != ilo && keep_hi != 0x7f800000u)
+                atomicMin(p.colmin + (long long)(ihi - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, keep_hi);
+            }
           }
         }
         tc_fence_before();
@@ -352,9 +421,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
           else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + buf * 8) : "memory");
         }
       }
-      if (row < p.Mq) {
-        const float d2 = best + __ldg(p.qn2 + row);
-        p.dmin[(long long)img * p.Mq + row] = sqrtf(fmaxf(d2, 0.f));
+      if (act) {
+        const float d2 = fmaxf(best + qn, 0.f);
+        p.dmin[(long long)img * p.Mq + row] = p.sym ? d2 : sqrtf(d2);
       }
     }
   }
@@ -434,7 +503,8 @@ static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {
 }
 
 int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long long Mq, const void* Bhi, const void* Blo,
-                      const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int* err_flag, cudaStream_t st) {
+                      const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int* err_flag, cudaStream_t st,
+                      int sym = 0, int q_img0 = 0, unsigned int* colmin = nullptr) {
   const bool bf16 = (precision == AC_PREC_BF16 || precision == AC_PREC_BF16X3);
   const bool x3 = (precision == AC_PREC_F16X3 || precision == AC_PREC_BF16X3);
   if (D % 8 != 0) return AC_ERR_UNSUPPORTED;  // TMA needs a 16-byte row pitch
@@ -454,7 +524,9 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.nseg = x3 ? 3 : 1;
   prm.n_mblocks = (int)ceil_div64(Mq, (long long)kTileM * G);
   prm.GM = g_tc_gm;
-  prm.total_units = (long long)prm.n_mblocks * nb_img;
+  prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin;
+  prm.KU = std::min(nb_img, nb_img / 2 + (kTileM * G - 1) / P + 1);
+  prm.total_units = (long long)prm.n_mblocks * (sym ? prm.KU : nb_img);
   prm.idesc_main = make_idesc(kTileM * G, wmain, bf16);
   prm.idesc_last = make_idesc(kTileM * G, wlast, bf16);
   const long long brows = (long long)nb_img * P;
@@ -489,6 +561,53 @@ extern "C" int ac_debug_set(int key, int value) {
   if (key == 0 && (value == 1 || value == 2)) { g_tc_cta_group = value; return AC_OK; }
   if (key == 1 && value >= 1) { g_tc_gm = value; return AC_OK; }
   return AC_ERR_INVALID;
+}
+
+__global__ void reduce_weights_sym_kernel(const float* __restrict__ rowmin, const float* __restrict__ colmin, long long Mq, int nb_img,
+                                          int Pq, int q_img0, float* __restrict__ w) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= Mq) return;
+  const int i = q_img0 + (int)(r / Pq);
+  float s = 0.f;
+  int cnt = 0;
+  for (int j = 0; j < nb_img; ++j) {
+    if (j == i) continue;
+    const float d2 = pair_owned(i, j, nb_img) ? __ldg(rowmin + (long long)j * Mq + r) : __ldg(colmin + (long long)j * Mq + r);
+    s += sqrtf(d2);   // same left-to-right order as the reference's torch.mean over the cat'ed columns
+    ++cnt;
+  }
+  w[r] = cnt > 0 ? s / (float)cnt : nanf("");
+}
+
+extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                               const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, float* rowmin_d2,
+                               float* colmin_d2, void* ws, size_t ws_bytes, ac_stream_t stream) {
+  if (!Qhi || !Bhi || !Qn2 || !Bn2 || !rowmin_d2 || !colmin_d2 || Mq < 0 || nb_img < 1 || P < 1 || D < 1 || q_img0 < 0)
+    return AC_ERR_INVALID;
+  if (precision < AC_PREC_F16 || precision > AC_PREC_BF16X3) return AC_ERR_UNSUPPORTED;  // tensor-core modes only
+  if (P < 32 || Mq % P != 0) return AC_ERR_UNSUPPORTED;  // a warp of 32 rows may span at most two query images
+  if (q_img0 + Mq / P > nb_img) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (Mq == 0) return AC_OK;
+  if (!ws || ws_bytes < 256) return AC_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  AC_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+  // column minima are accumulated with atomicMin on the fp32 bit pattern: start from a huge finite value
+  AC_CUDA(cudaMemsetAsync(colmin_d2, 0x7f, (size_t)(Mq / P) * nb_img * P * sizeof(float), st));
+  return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, rowmin_d2, (int*)ws, st, 1, q_img0,
+                           (unsigned int*)colmin_d2);
+}
+
+extern "C" int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
+                                     float* w, ac_stream_t stream) {
+  if (!rowmin_d2 || !colmin_d2 || !w || Mq < 0 || nb_img < 1 || Pq < 1 || q_img0 < 0) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  if (Mq == 0) return AC_OK;
+  reduce_weights_sym_kernel<<<(unsigned)((Mq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowmin_d2, colmin_d2, Mq, nb_img, Pq, q_img0, w);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
 }
 
 extern "C" size_t ac_min_dist_workspace_bytes(int64_t Mq, int nb_img, int P, int D, int precision) {

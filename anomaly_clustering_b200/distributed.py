@@ -14,6 +14,18 @@ import torch
 import torch.distributed as dist
 
 
+def pair_owned(i: int, j: int, n: int) -> bool:
+    """Host mirror of the kernel's pair-ownership rule (csrc/mindist_tc.cu: pair_owned)."""
+    d = (j - i) % n
+    if d == 0:
+        return False
+    if 2 * d < n:
+        return True
+    if 2 * d == n:
+        return i < j
+    return False
+
+
 def shard_bounds(n_items: int, world: int) -> List[Tuple[int, int]]:
     """Contiguous, balanced slices: the first n % world ranks get one extra item."""
     base, extra = divmod(n_items, world)
@@ -56,6 +68,29 @@ def all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None) -> t
     return torch.cat([buf[r * mx : r * mx + counts[r]] for r in range(world)], dim=0)
 
 
+def exchange_colmin(colmin: torch.Tensor, bounds: Sequence[Tuple[int, int]], P: int, group=None) -> torch.Tensor:
+    """Symmetric mode: rank r holds colmin [n_r, N*P] = (its images as BANK image, every global query
+    row); the owner of query rows [a*P, b*P) needs those columns from every rank.  All-to-all of the
+    column blocks -> [N, n_r*P] (bank image, local query row)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n_r = bounds[rank][1] - bounds[rank][0]
+    send = [colmin[:, a * P : b * P].contiguous() for a, b in bounds]
+    recv = [torch.empty((b - a, n_r * P), dtype=colmin.dtype, device=colmin.device) for a, b in bounds]
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv, send, group=group)
+    else:  # gloo (CPU tests) has no all_to_all for uneven splits: point-to-point exchange
+        recv[rank].copy_(send[rank])
+        reqs = []
+        for peer in range(world):
+            if peer == rank:
+                continue
+            reqs.append(dist.isend(send[peer], peer, group=group))
+            reqs.append(dist.irecv(recv[peer], peer, group=group))
+        for r in reqs:
+            r.wait()
+    return torch.cat(recv, dim=0)
+
+
 def run_path_sharded(
     local_features: Sequence[torch.Tensor],
     n_total: int,
@@ -67,6 +102,7 @@ def run_path_sharded(
     precision: str = "f16",
     group=None,
     compute=None,
+    symmetric: bool = True,
 ):
     """Unsupervised path over n_total images sharded by shard_bounds(); `local_features` are this
     rank's images.  Returns (alpha64_local [T,n_r,P], X_all [T,N,D], Dmat [T,N,N], w_local).
@@ -85,6 +121,8 @@ def run_path_sharded(
             alpha = staticmethod(ops.alpha)
             weighted_embed = staticmethod(ops.weighted_embed)
             pairwise_l2 = staticmethod(ops.pairwise_l2)
+            min_dist_sym = staticmethod(ops.min_dist_sym)
+            reduce_weights_sym = staticmethod(ops.reduce_weights_sym)
 
         compute = _Cuda
 
@@ -104,8 +142,17 @@ def run_path_sharded(
             lo=None if q.lo is None else all_gather_rows(q.lo, row_counts, group),
             n2=all_gather_rows(q.n2, row_counts, group),
         )
-    q_self = torch.arange(lo_i, hi_i, dtype=torch.int32, device=q.Z.device)
-    w = compute.min_distance_weights(q, bank, "unsupervised", precision, q_self=q_self)
+    if symmetric and precision != "f32" and P >= 32 and hasattr(compute, "min_dist_sym"):
+        # every unordered image pair is multiplied once, by the rank that owns the pair's first image;
+        # the column minima it produces for other ranks' query rows travel in one small all-to-all
+        pipeline._mark("mindist_begin")
+        rowmin, colmin = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision)
+        pipeline._mark("mindist_end")
+        colfull = exchange_colmin(colmin, bounds, P, group)
+        w = compute.reduce_weights_sym(rowmin, colfull, P, lo_i).reshape(q.n_img, P)
+    else:
+        q_self = torch.arange(lo_i, hi_i, dtype=torch.int32, device=q.Z.device)
+        w = compute.min_distance_weights(q, bank, "unsupervised", precision, q_self=q_self)
     a64, a32 = compute.alpha(w, list(taus))
     Z3 = q.Z.reshape(q.n_img, P, q.D)
     X_loc = torch.stack([compute.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)  # [n_r, T, D]

@@ -178,6 +178,35 @@ def min_dist(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, 
     return dmin
 
 
+def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str):
+    """Symmetric self-bank form: (rowmin_d2 [nb_img, Mq], colmin_d2 [Mq/P, nb_img*P]) squared distances."""
+    lib = _lib.load()
+    _need_cuda(Qhi, Bhi)
+    prec = _lib.PRECISIONS[precision]
+    Mq, D = Qhi.shape
+    assert Bhi.shape == (nb_img * P, D) and Qhi.is_contiguous() and Bhi.is_contiguous()
+    rowmin = torch.empty(nb_img, Mq, dtype=torch.float32, device=Qhi.device)
+    colmin = torch.empty(Mq // P, nb_img * P, dtype=torch.float32, device=Qhi.device)
+    ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
+    rc = lib.ac_min_dist_sym(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
+                             _ptr(rowmin), _ptr(colmin), _ptr(ws), ws_bytes, _stream())
+    check(rc, "ac_min_dist_sym")
+    _count(1)
+    return rowmin, colmin
+
+
+def reduce_weights_sym(rowmin: torch.Tensor, colfull: torch.Tensor, Pq: int, q_img0: int) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(rowmin, colfull)
+    nb_img, Mq = rowmin.shape
+    assert colfull.shape == rowmin.shape and colfull.is_contiguous() and rowmin.is_contiguous()
+    w = torch.empty(Mq, dtype=torch.float32, device=rowmin.device)
+    check(lib.ac_reduce_weights_sym(_ptr(rowmin), _ptr(colfull), Mq, nb_img, Pq, q_img0, _ptr(w), _stream()), "ac_reduce_weights_sym")
+    _count(1)
+    return w
+
+
 def reduce_weights(dmin: torch.Tensor, Pq: int, q_self: Optional[torch.Tensor], mode: str) -> torch.Tensor:
     lib = _lib.load()
     _need_cuda(dmin, q_self)

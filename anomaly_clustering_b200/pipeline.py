@@ -20,6 +20,10 @@ import torch
 
 from . import ops
 
+# Unsupervised self-bank runs multiply every unordered image pair once (ac_min_dist_sym); set to
+# False to force the straightforward all-pairs kernel (bench.py --no-symmetry, A/B tests).
+SYMMETRIC = True
+
 # bench.py sets this to a list to collect (tag, cuda event) marks at stage boundaries
 PROFILE = None
 
@@ -126,6 +130,12 @@ def min_distance_weights(
 ):
     """Stage 2: w [Nq, P].  mode 'unsupervised' = mean over bank images != self (utils.py:222-227),
     'supervised' = min over bank images (utils.py:230-237).  q_self[i] = bank index of query image i."""
+    if (mode == "unsupervised" and SYMMETRIC and q is bank and precision != "f32" and q.P >= 32 and not return_dmin
+            and q_self is None):
+        _mark("mindist_begin")
+        rowmin, colmin = ops.min_dist_sym(q.hi, q.lo, q.n2, 0, q.hi, q.lo, q.n2, q.n_img, q.P, precision)
+        _mark("mindist_end")
+        return ops.reduce_weights_sym(rowmin, colmin, q.P, 0).reshape(q.n_img, q.P)
     _mark("mindist_begin")
     if precision == "f32":
         dmin = ops.min_dist(q.Z, None, None, bank.Z, None, None, bank.n_img, bank.P, "f32")

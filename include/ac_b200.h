@@ -9,7 +9,8 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns every buffer,
- *     including the workspace; the library allocates nothing persistent and keeps no global state;
+ *     including the workspace; the library allocates no device memory and keeps no global state
+ *     except a small mutex-protected host cache of launch plans (pure functions of the shapes);
  *   - every call is asynchronous and ordered on `stream` (a cudaStream_t); no hidden synchronisation;
  *   - return value: 0 on success, a negative AC_ERR_* code otherwise (never throws, never aborts);
  *   - there is NO CPU fallback: on anything that is not compute capability 10.x the calls fail with
@@ -127,6 +128,26 @@ int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, 
  * q_self: [ceil(Mq/Pq)] int32 bank-image index of each query image, -1 or NULL = none. */
 int ac_reduce_weights(const float* dmin, int64_t Mq, int nb_img, int Pq, const int32_t* q_self,
                       int mode, float* w, ac_stream_t stream);
+
+/* Symmetric form of the unsupervised case: the queries are images
+ * [q_img0, q_img0 + Mq/P) OF the bank (Q = B + q_img0*P*D), and torch.cdist(Z[i], Z[j]) is the transpose
+ * of torch.cdist(Z[j], Z[i]) (utils.py:226), so every unordered image pair {i, j} is multiplied ONCE: by the
+ * query image that "owns" it (j within the next floor((N-1)/2) images after i in circular order).  The owner's
+ * tile yields both
+ *   rowmin_d2[j*Mq + r]              = min_c |q_r - b_(j,c)|^2     for query rows r of image i   (plain stores), and
+ *   colmin_d2[(i-q_img0)*nb_img*P + j*P + c] = min_{r in image i} |q_r - b_(j,c)|^2             (atomicMin),
+ * i.e. the distance of patch (j,c) to its nearest patch of image i.  Values are SQUARED distances; entries of
+ * pairs that are not owned are undefined (rowmin) / huge (colmin).  With a single rank (Mq = nb_img*P) colmin is
+ * already laid out as [bank image, query row]; sharded runs exchange column blocks (all-to-all) first.
+ * Tensor-core precisions only; needs P >= 32 and Mq % P == 0, else AC_ERR_UNSUPPORTED (use ac_min_dist). */
+int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                    const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, float* rowmin_d2,
+                    float* colmin_d2, void* ws, size_t ws_bytes, ac_stream_t stream);
+
+/* w[r] = mean over bank images j != i(r) of sqrt(owned(i,j) ? rowmin_d2[j,r] : colmin_d2[j,r]); both arrays
+ * [nb_img, Mq], i(r) = q_img0 + r / Pq.  Replaces utils.py:227 for the symmetric form. */
+int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
+                          float* w, ac_stream_t stream);
 
 /* ---- stage 3 -----------------------------------------------------------------------------------
  * alpha[t, i, :] = softmax_p(w[i, :] / tau_t) in float64, max-subtracted (identical to

@@ -16,6 +16,17 @@ from anomaly_clustering_b200 import distributed, pipeline
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_pair_ownership_covers_every_pair_once():
+    for n in (1, 2, 3, 4, 5, 8, 9, 100):
+        for i in range(n):
+            assert not distributed.pair_owned(i, i, n)
+            for j in range(i + 1, n):
+                assert distributed.pair_owned(i, j, n) != distributed.pair_owned(j, i, n)
+        if n > 1:
+            per_image = [sum(distributed.pair_owned(i, j, n) for j in range(n)) for i in range(n)]
+            assert max(per_image) - min(per_image) <= 1     # balanced: each image owns ~(n-1)/2 pairs
+
+
 def test_shard_bounds_and_lpt():
     assert distributed.shard_bounds(100, 8) == [(0, 13), (13, 26), (26, 39), (39, 52), (52, 64), (64, 76), (76, 88), (88, 100)]
     assert distributed.shard_bounds(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
@@ -52,6 +63,31 @@ class _OracleCompute:
         return w
 
     @staticmethod
+    def min_dist_sym(Qhi, Qlo, Qn2, q_img0, Bhi, Blo, Bn2, nb_img, P, precision):
+        """What ac_min_dist_sym produces: squared minima only for the pairs the query image owns."""
+        nq = Qhi.shape[0] // P
+        d2 = torch.cdist(Qhi.double(), Bhi.double()).pow(2).float().reshape(nq, P, nb_img, P)
+        rowmin = torch.full((nb_img, nq * P), float("nan"))
+        colmin = torch.full((nq, nb_img * P), 3.0e38)
+        for il in range(nq):
+            for j in range(nb_img):
+                if distributed.pair_owned(q_img0 + il, j, nb_img):
+                    blk = d2[il, :, j, :]
+                    rowmin[j, il * P:(il + 1) * P] = blk.min(dim=1)[0]
+                    colmin[il, j * P:(j + 1) * P] = blk.min(dim=0)[0]
+        return rowmin, colmin
+
+    @staticmethod
+    def reduce_weights_sym(rowmin, colfull, P, q_img0):
+        nb_img, Mq = rowmin.shape
+        w = torch.empty(Mq)
+        for r in range(Mq):
+            i = q_img0 + r // P
+            vals = [(rowmin[j, r] if distributed.pair_owned(i, j, nb_img) else colfull[j, r]).sqrt() for j in range(nb_img) if j != i]
+            w[r] = torch.stack(vals).mean()
+        return w
+
+    @staticmethod
     def alpha(w, taus):
         from oracle import restated
 
@@ -81,7 +117,10 @@ def _worker(rank, world, port, n_total, tmp):
     allr = distributed.all_gather_rows(local, [b - a for a, b in distributed.shard_bounds(n_total, world)])
     assert torch.equal(allr[:, 0], torch.arange(n_total, dtype=torch.float32))
     a64, X, Dm, w = distributed.run_path_sharded([f[lo:hi] for f in feats], n_total, 3, 1, 32, 64, [1.0, 2.0], precision="f16",
-                                                 compute=_OracleCompute)
+                                                 compute=_OracleCompute, symmetric=True)
+    _, _, _, w_full = distributed.run_path_sharded([f[lo:hi] for f in feats], n_total, 3, 1, 32, 64, [1.0], precision="f16",
+                                                   compute=_OracleCompute, symmetric=False)
+    assert (w - w_full).abs().max().item() <= 1e-4      # symmetric exchange == straightforward all-pairs
     np.savez(os.path.join(tmp, "r%d.npz" % rank), a=a64.numpy(), X=X.numpy(), D=Dm.numpy(), w=w.numpy())
     dist.destroy_process_group()
 

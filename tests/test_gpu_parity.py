@@ -200,6 +200,54 @@ def test_mindist_vs_oracle_config2_width(precision, tol):
     assert rel <= tol, rel
 
 
+@pytest.mark.parametrize("n,P,D", [(7, 100, 256), (6, 784, 512), (2, 64, 64), (9, 36, 128), (5, 260, 320)])
+@pytest.mark.parametrize("precision", ["f16", "bf16x3"])
+def test_mindist_symmetric_equals_all_pairs(n, P, D, precision):
+    """ac_min_dist_sym multiplies every unordered image pair once (row-min + column-min of the same
+    tile); the resulting w must equal the straightforward all-pairs kernel's."""
+    gen = torch.Generator().manual_seed(n * 31 + P)
+    base = torch.randn(1, P, D, generator=gen)
+    Z = (base + 0.5 * torch.randn(n, P, D, generator=gen)).cuda()
+    ps = pipeline.patchset_from_Z(Z, precision)
+    try:
+        pipeline.SYMMETRIC = False
+        w_full = pipeline.min_distance_weights(ps, ps, "unsupervised", precision)
+        pipeline.SYMMETRIC = True
+        w_sym = pipeline.min_distance_weights(ps, ps, "unsupervised", precision)
+    finally:
+        pipeline.SYMMETRIC = True
+    assert torch.isfinite(w_sym).all()
+    assert ((w_sym - w_full).abs() / w_full.abs().clamp_min(1e-3)).max().item() <= 2e-4
+    # and against the exact fp64 weights of the same operands
+    op = (ps.hi.double() + (ps.lo.double() if ps.lo is not None else 0.0)).cpu().reshape(n, P, D)
+    want = torch.empty(n, P, dtype=torch.float64)
+    for i in range(n):
+        cols = [torch.cdist(op[i], op[j]).min(dim=1)[0] for j in range(n) if j != i]
+        want[i] = torch.stack(cols, 1).mean(1)
+    assert ((w_sym.double().cpu() - want).abs() / want).max().item() <= 5e-4
+
+
+def test_mindist_symmetric_sharded_slices():
+    """Two query slices of one bank (what two ranks compute) + the column-block exchange reproduce the
+    single-slice result."""
+    from anomaly_clustering_b200 import distributed
+
+    n, P, D = 7, 96, 128
+    gen = torch.Generator().manual_seed(5)
+    Z = (torch.randn(1, P, D, generator=gen) + 0.5 * torch.randn(n, P, D, generator=gen)).cuda()
+    ps = pipeline.patchset_from_Z(Z, "f16")
+    w_one = pipeline.min_distance_weights(ps, ps, "unsupervised", "f16")
+    bounds = distributed.shard_bounds(n, 2)
+    parts = []
+    for a, b in bounds:
+        sl = slice(a * P, b * P)
+        parts.append(ops.min_dist_sym(ps.hi[sl], None, ps.n2[sl], a, ps.hi, None, ps.n2, n, P, "f16"))
+    for r, (a, b) in enumerate(bounds):
+        colfull = torch.cat([parts[s][1][:, a * P:b * P] for s in range(2)], dim=0).contiguous()
+        w = ops.reduce_weights_sym(parts[r][0], colfull, P, a).reshape(b - a, P)
+        assert ((w - w_one[a:b]).abs() / w_one[a:b]).max().item() <= 2e-4
+
+
 # ------------------------------------------------------------------------------- stage 3
 def test_alpha_golden(golden_dir):
     g = gload(golden_dir, "alpha_small")
