@@ -222,10 +222,13 @@ __device__ __forceinline__ bool decode_unit(const TcParams& p, long long u, int&
   const int k = (int)(rem / gm_cur);
   mb = mg * p.GM + (int)(rem - (long long)k * gm_cur);
   if (!p.sym) { img = k; return true; }
+  // sym: the bank image is the k-th image after the first image of the raster GROUP, so the query
+  // blocks of a group walk the same bank images together (L2 reuse); blocks that do not own the pair skip
+  const int ig = p.q_img0 + (int)(((long long)mg * p.GM * (kTileM * G)) / p.P);
+  img = (ig + 1 + k) % p.nb_img;
   const long long r0 = (long long)mb * (kTileM * G);
   const long long r1 = min(p.Mq, r0 + kTileM * G) - 1;
   const int i0 = p.q_img0 + (int)(r0 / p.P), i1 = p.q_img0 + (int)(r1 / p.P);
-  img = (i0 + 1 + k) % p.nb_img;
   for (int i = i0; i <= i1; ++i)
     if (pair_owned(i, img, p.nb_img)) return true;
   return false;
@@ -525,7 +528,8 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.n_mblocks = (int)ceil_div64(Mq, (long long)kTileM * G);
   prm.GM = g_tc_gm;
   prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin;
-  prm.KU = std::min(nb_img, nb_img / 2 + (kTileM * G - 1) / P + 1);
+  // bank images a raster group of GM query blocks can own: N/2 after each of the images it spans
+  prm.KU = std::min(nb_img, nb_img / 2 + (int)(((long long)prm.GM * kTileM * G - 1) / P) + 1);
   prm.total_units = (long long)prm.n_mblocks * (sym ? prm.KU : nb_img);
   prm.idesc_main = make_idesc(kTileM * G, wmain, bf16);
   prm.idesc_last = make_idesc(kTileM * G, wlast, bf16);

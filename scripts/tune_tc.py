@@ -43,3 +43,22 @@ for g in (1, 2):
     run(2)
     ms = run(12)
     print("cta_group=%d GM=16  %.2f ms  %.0f TFLOP/s" % (g, ms, flops / ms / 1e9), flush=True)
+
+
+def run_sym(reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.min_dist_sym(ps.hi, None, ps.n2, 0, ps.hi, None, ps.n2, n, P, "f16")
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+lib.ac_debug_set(0, 2)
+for v in (4, 8, 12, 16, 24, 32):
+    lib.ac_debug_set(1, v)
+    run_sym(2)
+    ms = run_sym(12)
+    print("SYM GM=%d  %.2f ms  %.0f TFLOP/s executed, %.0f algorithmic" % (v, ms, 0.5 * flops / ms / 1e9, flops / ms / 1e9), flush=True)
+lib.ac_debug_set(1, 16)
