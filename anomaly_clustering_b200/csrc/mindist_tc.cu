@@ -212,6 +212,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 
 // unit index -> (query block, bank image); false when the unit carries no work (sym mode: no row of
 // the block owns the pair).  Every warp role evaluates this identically, so skipped units touch no barrier.
+// r[i] = this lane's value for column i (32 columns x 32 lanes).  Returns min over all lanes of
+// column `lane`: at each butterfly level a lane keeps the half of the columns whose index bit matches
+// its own lane bit and hands the other half to its partner.
+__device__ __forceinline__ float warp_transpose_min(float (&r)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = up ? r[i + off] : r[i];
+      const float send = up ? r[i] : r[i + off];
+      r[i] = fminf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+    }
+  }
+  return r[0];
+}
+
 template <int G>
 __device__ __forceinline__ bool decode_unit(const TcParams& p, long long u, int& mb, int& img) {
   const int per_mb = p.sym ? p.KU : p.nb_img;
@@ -388,32 +405,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
               for (int i = 0; i < 16; ++i) best = fminf(best, fmaf(-2.f, __uint_as_float(v1[i]), bn[c0 + 16 + i]));
             }
           } else {
-            // row-min as above + column-min over the rows of this warp: non-negative floats order like
-            // their bit patterns, so one REDUX.MIN.U32 per column does the 32-row reduction; lane i keeps
-            // column c0+i and the warp issues one coalesced atomicMin per 32 columns
-            unsigned int keep_lo = 0x7f800000u, keep_hi = 0x7f800000u;
-            const bool in_lo = act && (irow == ilo), in_hi = act && (irow == ihi) && (ihi != ilo);
+            // row-min as above + column-min over the 32 rows of this warp.  A butterfly "transpose
+            // reduction" leaves the min of column c0+l in lane l after 31 shuffles for 32 columns
+            // (REDUX.MIN measured ~110 cycles per column here; this is ~4 instructions per column);
+            // then one coalesced atomicMin per 32 columns.  Non-negative floats order like their bits.
+            float e[32];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (h == 1 && !two) break;
+            for (int i = 0; i < 16; ++i) {
+              const float part = fmaf(-2.f, __uint_as_float(v0[i]), bn[c0 + i]);
+              best = fminf(best, part);
+              e[i] = fmaxf(part + qn, 0.f);
+            }
+            if (two) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float part = fmaf(-2.f, __uint_as_float(h ? v1[i] : v0[i]), bn[c0 + h * 16 + i]);
+                const float part = fmaf(-2.f, __uint_as_float(v1[i]), bn[c0 + 16 + i]);
                 best = fminf(best, part);
-                const unsigned int e = __float_as_uint(fmaxf(part + qn, 0.f));
-                const unsigned int m_lo = __reduce_min_sync(0xffffffffu, in_lo ? e : 0x7f800000u);
-                if (lane == h * 16 + i) keep_lo = m_lo;
-                if (ihi != ilo) {   // warp-uniform: the warp straddles two query images
-                  const unsigned int m_hi = __reduce_min_sync(0xffffffffu, in_hi ? e : 0x7f800000u);
-                  if (lane == h * 16 + i) keep_hi = m_hi;
-                }
+                e[16 + i] = fmaxf(part + qn, 0.f);
               }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) e[16 + i] = INFINITY;
             }
+            const bool in_lo = act && (irow == ilo), in_hi = act && (irow == ihi) && (ihi != ilo);
             const int c = c0 + lane;
-            if (c < valid) {
-              if (keep_lo != 0x7f800000u) atomicMin(p.colmin + (long long)(ilo - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, keep_lo);
-              if (ihi != ilo && keep_hi != 0x7f800000u)
-                atomicMin(p.colmin + (long long)(ihi - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, keep_hi);
+            {
+              float r[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = in_lo ? e[i] : INFINITY;
+              const float m = warp_transpose_min(r, lane);
+              if (c < valid && m < 3.0e38f)
+                atomicMin(p.colmin + (long long)(ilo - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, __float_as_uint(m));
+            }
+            if (ihi != ilo) {   // warp-uniform: this warp's rows straddle two query images
+              float r[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = in_hi ? e[i] : INFINITY;
+              const float m = warp_transpose_min(r, lane);
+              if (c < valid && m < 3.0e38f)
+                atomicMin(p.colmin + (long long)(ihi - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, __float_as_uint(m));
             }
           }
         }
