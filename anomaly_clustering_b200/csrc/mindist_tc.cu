@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 namespace ac {
 
@@ -54,6 +55,7 @@ struct __align__(64) TcParams {
   int q_img0;                // global image index of query row 0 (query slice of a sharded run)
   int KU;                    // units per query block in sym mode
   unsigned int* colmin;      // [nq_img, nb_img*P] squared distances (fp32 bits), atomicMin target
+  const int2* units;         // sym mode: explicit (query block, bank image) list in raster order
 };
 
 // Ownership of the unordered pair {i, j} of N images: the image that sees the other one within the
@@ -231,24 +233,23 @@ __device__ __forceinline__ float warp_transpose_min(float (&r)[32], int lane) {
 
 template <int G>
 __device__ __forceinline__ bool decode_unit(const TcParams& p, long long u, int& mb, int& img) {
-  const int per_mb = p.sym ? p.KU : p.nb_img;
+  if (p.sym) {
+    // compact host-built list (only units that carry work), so all CTA pairs stay in lock-step on the
+    // same few bank images and query blocks -- skipped slots would let them drift apart and thrash L2
+    const int2 un = __ldg(p.units + u);
+    mb = un.x;
+    img = un.y;
+    return true;
+  }
+  const int per_mb = p.nb_img;
   const long long per_group = (long long)p.GM * per_mb;
   const int mg = (int)(u / per_group);
   const long long rem = u - (long long)mg * per_group;
   const int gm_cur = min(p.GM, p.n_mblocks - mg * p.GM);
   const int k = (int)(rem / gm_cur);
   mb = mg * p.GM + (int)(rem - (long long)k * gm_cur);
-  if (!p.sym) { img = k; return true; }
-  // sym: the bank image is the k-th image after the first image of the raster GROUP, so the query
-  // blocks of a group walk the same bank images together (L2 reuse); blocks that do not own the pair skip
-  const int ig = p.q_img0 + (int)(((long long)mg * p.GM * (kTileM * G)) / p.P);
-  img = (ig + 1 + k) % p.nb_img;
-  const long long r0 = (long long)mb * (kTileM * G);
-  const long long r1 = min(p.Mq, r0 + kTileM * G) - 1;
-  const int i0 = p.q_img0 + (int)(r0 / p.P), i1 = p.q_img0 + (int)(r1 / p.P);
-  for (int i = i0; i <= i1; ++i)
-    if (pair_owned(i, img, p.nb_img)) return true;
-  return false;
+  img = k;
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -537,7 +538,7 @@ static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {
 
 int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long long Mq, const void* Bhi, const void* Blo,
                       const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int* err_flag, cudaStream_t st,
-                      int sym = 0, int q_img0 = 0, unsigned int* colmin = nullptr) {
+                      int sym = 0, int q_img0 = 0, unsigned int* colmin = nullptr, void* unit_ws = nullptr, size_t unit_ws_bytes = 0) {
   const bool bf16 = (precision == AC_PREC_BF16 || precision == AC_PREC_BF16X3);
   const bool x3 = (precision == AC_PREC_F16X3 || precision == AC_PREC_BF16X3);
   if (D % 8 != 0) return AC_ERR_UNSUPPORTED;  // TMA needs a 16-byte row pitch
@@ -557,10 +558,37 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.nseg = x3 ? 3 : 1;
   prm.n_mblocks = (int)ceil_div64(Mq, (long long)kTileM * G);
   prm.GM = g_tc_gm;
-  prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin;
+  prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin; prm.units = nullptr;
   // bank images a raster group of GM query blocks can own: N/2 after each of the images it spans
   prm.KU = std::min(nb_img, nb_img / 2 + (int)(((long long)prm.GM * kTileM * G - 1) / P) + 1);
-  prm.total_units = (long long)prm.n_mblocks * (sym ? prm.KU : nb_img);
+  prm.total_units = (long long)prm.n_mblocks * nb_img;
+  if (sym) {
+    // raster order: groups of GM query blocks; inside a group walk the bank images the group owns and,
+    // per bank image, every block of the group that owns the pair (blocks sharing a bank image run together)
+    std::vector<int2> units;
+    units.reserve((size_t)prm.n_mblocks * (nb_img / 2 + 2));
+    const long long rows_per_mb = (long long)kTileM * G;
+    for (int mg = 0; mg * prm.GM < prm.n_mblocks; ++mg) {
+      const int gm_cur = std::min(prm.GM, prm.n_mblocks - mg * prm.GM);
+      const int ig = q_img0 + (int)(((long long)mg * prm.GM * rows_per_mb) / P);
+      for (int k = 0; k < prm.KU; ++k) {
+        const int img = (ig + 1 + k) % nb_img;
+        for (int mi = 0; mi < gm_cur; ++mi) {
+          const int mb = mg * prm.GM + mi;
+          const long long r0 = (long long)mb * rows_per_mb, r1 = std::min<long long>(Mq, r0 + rows_per_mb) - 1;
+          const int i0 = q_img0 + (int)(r0 / P), i1 = q_img0 + (int)(r1 / P);
+          bool work = false;
+          for (int i = i0; i <= i1 && !work; ++i) work = pair_owned(i, img, nb_img);
+          if (work) units.push_back(make_int2(mb, img));
+        }
+      }
+    }
+    prm.total_units = (long long)units.size();
+    if (prm.total_units == 0) return AC_OK;
+    if (!unit_ws || unit_ws_bytes < units.size() * sizeof(int2)) return AC_ERR_WORKSPACE;
+    AC_CUDA(cudaMemcpyAsync(unit_ws, units.data(), units.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    prm.units = (const int2*)unit_ws;
+  }
   prm.idesc_main = make_idesc(kTileM * G, wmain, bf16);
   prm.idesc_last = make_idesc(kTileM * G, wlast, bf16);
   const long long brows = (long long)nb_img * P;
@@ -630,7 +658,7 @@ extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn
   // column minima are accumulated with atomicMin on the fp32 bit pattern: start from a huge finite value
   AC_CUDA(cudaMemsetAsync(colmin_d2, 0x7f, (size_t)(Mq / P) * nb_img * P * sizeof(float), st));
   return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, rowmin_d2, (int*)ws, st, 1, q_img0,
-                           (unsigned int*)colmin_d2);
+                           (unsigned int*)colmin_d2, (char*)ws + 256, ws_bytes - 256);
 }
 
 extern "C" int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
@@ -645,8 +673,11 @@ extern "C" int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin
 }
 
 extern "C" size_t ac_min_dist_workspace_bytes(int64_t Mq, int nb_img, int P, int D, int precision) {
-  (void)Mq; (void)nb_img; (void)P; (void)D; (void)precision;
-  return 256;  // pipeline-watchdog flag
+  (void)D; (void)precision;
+  // 256 B pipeline-watchdog flag + (symmetric form) the raster list of (query block, bank image) units
+  const long long mblocks = (Mq + 127) / 128;
+  const long long per_mb = std::min<long long>(nb_img, nb_img / 2 + 64 * 256 / std::max(1, P) + 2);
+  return 256 + (size_t)(mblocks * per_mb) * sizeof(int2);
 }
 
 extern "C" int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
