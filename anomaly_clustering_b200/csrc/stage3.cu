@@ -180,6 +180,41 @@ __global__ void __launch_bounds__(256) pairwise_l2_kernel(const float* __restric
     }
 }
 
+// small N (one category: N ~ 100): one warp per (i, j >= i) pair, X stays L2-resident; the tiled
+// kernel above would run only ~N^2/2048 CTAs
+__global__ void __launch_bounds__(256) pairwise_l2_warp_kernel(const float* __restrict__ X, int N, int D, float* __restrict__ Dm) {
+  const long long w = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)N * N) return;
+  const int i = (int)(w / N), j = (int)(w - (long long)i * N);
+  if (j < i) return;
+  const int lane = threadIdx.x & 31;
+  const float* xi = X + (long long)i * D;
+  const float* xj = X + (long long)j * D;
+  float acc = 0.f;
+  if ((D & 3) == 0) {
+    for (int d = lane * 4; d < D; d += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xi + d));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(xj + d));
+      float t;
+      t = a.x - b.x; acc = fmaf(t, t, acc);
+      t = a.y - b.y; acc = fmaf(t, t, acc);
+      t = a.z - b.z; acc = fmaf(t, t, acc);
+      t = a.w - b.w; acc = fmaf(t, t, acc);
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) {
+      const float t = __ldg(xi + d) - __ldg(xj + d);
+      acc = fmaf(t, t, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float dd = (i == j) ? 0.f : sqrtf(acc);
+    Dm[(long long)i * N + j] = dd;
+    Dm[(long long)j * N + i] = dd;
+  }
+}
+
 }  // namespace ac
 
 using namespace ac;
@@ -254,8 +289,13 @@ extern "C" int ac_pairwise_l2(const float* X, int N, int D, float* Dmat, ac_stre
   int rc = check_device();
   if (rc) return rc;
   if (N == 0) return AC_OK;
-  dim3 grid(ceil_div(N, 32), ceil_div(N, 32));
-  pairwise_l2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, Dmat);
+  if (N <= 384) {
+    const long long warps = (long long)N * N;
+    pairwise_l2_warp_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(X, N, D, Dmat);
+  } else {
+    dim3 grid(ceil_div(N, 32), ceil_div(N, 32));
+    pairwise_l2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, N, D, Dmat);
+  }
   AC_LAUNCH_CHECK();
   return AC_OK;
 }

@@ -284,6 +284,11 @@ def test_weighted_embed_and_pairwise_vs_oracle(golden_dir):
     want = restated.pairwise_euclidean(X.numpy())
     assert rel_l2(D, want) <= 1e-6
     assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+    # large N takes the tiled kernel
+    X = torch.randn(500, 129, generator=gen)
+    D = ops.pairwise_l2(X.cuda()).cpu().numpy()
+    assert rel_l2(D, restated.pairwise_euclidean(X.numpy())) <= 1e-6
+    assert np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
     # odd sizes
     X = torch.randn(5, 7, generator=gen)
     assert rel_l2(ops.pairwise_l2(X.cuda()).cpu().numpy(), restated.pairwise_euclidean(X.numpy())) <= 1e-6
