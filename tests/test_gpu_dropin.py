@@ -1,0 +1,86 @@
+"""GPU: the reference's call sequence through the mirror classes (drop-in surface), end to end with a
+random-init backbone whose forward stays in torch."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from anomaly_clustering_b200 import backbones, driver, io  # noqa: E402
+from anomaly_clustering_b200.patchcore import common, patchcore, utils  # noqa: E402
+from oracle import restated  # noqa: E402
+
+
+def _images(n, seed=0, size=224):
+    gen = torch.Generator().manual_seed(seed)
+    base = torch.randn(1, 3, size, size, generator=gen)
+    x = base + 0.3 * torch.randn(n, 3, size, size, generator=gen)
+    for i in range(n):
+        if i % 2:
+            x[i, :, 60:100, 80:140] += 2.0
+    return x
+
+
+def test_anomaly_clustering_core_wideresnet50_matches_oracle():
+    """BASELINE config 1 pipeline: WRN50 layer2+layer3 hooks -> _embed (1024 -> 1024) -> Matrix_Alpha."""
+    dev = torch.device("cuda")
+    net = backbones.load("wideresnet50")
+    core = patchcore.AnomalyClusteringCore(dev).load(
+        backbone=net, layers_to_extract_from=["layer2", "layer3"], device=dev, input_shape=(3, 224, 224),
+        pretrain_embed_dimension=1024, target_embed_dimension=1024, patchsize=3)
+    imgs = _images(5)
+    rows, shapes = core._embed(imgs[:2], "unsupervised", provide_patch_shapes=True)     # reference return convention
+    assert isinstance(rows, list) and len(rows) == 2 * 784 and rows[0].shape == (1024,)
+    assert shapes == [[28, 28], [14, 14]]
+    feats = [f.float().cpu() for f in core._features(imgs.to(dev))]
+    assert feats[0].shape == (5, 512, 28, 28) and feats[1].shape == (5, 1024, 14, 14)
+    Zw = restated.embed(feats, 3, 1, 1024, 1024)
+    assert np.abs(np.stack(rows) - Zw[: 2 * 784].numpy()).max() <= 2e-5
+    Z = torch.stack([torch.from_numpy(np.stack(core._embed(imgs[i:i + 1], "unsupervised"))) for i in range(5)])   # main.py:266-267
+    alpha = utils.Matrix_Alpha_Unsupervised(1.0, 1, Z, dev)
+    assert alpha.dtype == torch.float64 and alpha.shape == (5, 784)
+    want = restated.matrix_alpha_unsupervised(1.0, Zw.reshape(5, 784, 1024))
+    assert (alpha.cpu() - want).abs().max().item() <= 1e-3
+    w0 = utils.Weight_Distance_Unsupervised(Z, 0, dev)
+    assert (w0.cpu() - restated.weight_distance_unsupervised(Zw.reshape(5, 784, 1024))[0]).abs().max().item() <= 5e-2
+    a_sup = utils.Matrix_Alpha_Supervised(2.0, 1, Z[:3], Z[3:], dev)
+    want_sup = restated.matrix_alpha_supervised(2.0, Zw.reshape(5, 784, 1024)[:3], Zw.reshape(5, 784, 1024)[3:])
+    assert (a_sup.cpu() - want_sup).abs().max().item() <= 1e-3
+
+
+def test_mirror_modules_standalone():
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 8, 10, 10, generator=gen)
+    pm = patchcore.PatchMaker(3, stride=1)
+    u, grid = pm.patchify(x.to(dev), return_spatial_info=True)
+    uw, gw = restated.patchify(x, 3, 1)
+    assert grid == gw and torch.equal(u.cpu(), uw.contiguous())
+    feats = [torch.randn(50, 8, 3, 3, generator=gen), torch.randn(50, 16, 3, 3, generator=gen)]
+    pre = common.Preprocessing([8, 16], 24)([f.to(dev) for f in feats])
+    agg = common.Aggregator(target_dim=10)(pre)
+    assert (pre.cpu() - restated.preprocessing_forward(feats, 24)).abs().max().item() <= 1e-6
+    assert (agg.cpu() - restated.aggregator_forward(restated.preprocessing_forward(feats, 24), 10)).abs().max().item() <= 1e-6
+
+
+def test_make_category_data_vit_writes_reference_pickle(tmp_path):
+    """DINO ViT-S/8 shape (random init): driver == oracle, tau list from one pass, pickle layout."""
+    dev = torch.device("cuda")
+    net = backbones.load("dino_vitsmall8")
+    imgs = _images(4, seed=3)
+    loader = [{"image": imgs[i:i + 1], "is_anomaly": torch.tensor([i % 2])} for i in range(4)]   # batch_size=1 like main.py:211
+    layers = ["blocks.10", "blocks.11"]
+    res = driver.make_category_data(None, "bottle", 512, 1024, ["dino_vitsmall8"], layers, 3, str(tmp_path), tau=[1.0, 2.0],
+                                    supervised="unsupervised", test_dataloader=loader, backbone=net, device=dev)
+    assert len(res) == 2
+    agg = common.NetworkFeatureAggregator(net, layers, dev)
+    feats = [agg(imgs.to(dev))[l].float().cpu() for l in layers]
+    assert feats[0].shape == (4, 785, 384)
+    for (alpha, X), tau in zip(res, [1.0, 2.0]):
+        _, _, a_w, X_w, _ = restated.full_path(feats, 3, 1, 512, 1024, tau, "unsupervised")
+        assert alpha.shape == (4, 1, 784) and alpha.dtype == torch.float32
+        assert (alpha.squeeze(1).cpu().double() - a_w).abs().max().item() <= 1e-3
+        assert np.linalg.norm(X - X_w) / np.linalg.norm(X_w) <= 1e-3
+        a_l, X_l = io.load_matrix_alpha_X(str(tmp_path / ("blocks.10_blocks.11_512_1024_%s_1.0" % float(tau))
+                                              / "matrix_alpha_X_bottle_unsupervised.pickle"))
+        assert np.array_equal(X_l, X) and torch.equal(a_l, alpha.cpu())
