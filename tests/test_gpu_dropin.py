@@ -28,15 +28,23 @@ def test_anomaly_clustering_core_wideresnet50_matches_oracle():
     core = patchcore.AnomalyClusteringCore(dev).load(
         backbone=net, layers_to_extract_from=["layer2", "layer3"], device=dev, input_shape=(3, 224, 224),
         pretrain_embed_dimension=1024, target_embed_dimension=1024, patchsize=3)
+    torch.backends.cudnn.allow_tf32 = False      # the backbone is torch: keep its features bit-stable across calls
+    torch.backends.cuda.matmul.allow_tf32 = False
     imgs = _images(5)
     rows, shapes = core._embed(imgs[:2], "unsupervised", provide_patch_shapes=True)     # reference return convention
     assert isinstance(rows, list) and len(rows) == 2 * 784 and rows[0].shape == (1024,)
     assert shapes == [[28, 28], [14, 14]]
-    feats = [f.float().cpu() for f in core._features(imgs.to(dev))]
-    assert feats[0].shape == (5, 512, 28, 28) and feats[1].shape == (5, 1024, 14, 14)
-    Zw = restated.embed(feats, 3, 1, 1024, 1024)
-    assert np.abs(np.stack(rows) - Zw[: 2 * 784].numpy()).max() <= 2e-5
-    Z = torch.stack([torch.from_numpy(np.stack(core._embed(imgs[i:i + 1], "unsupervised"))) for i in range(5)])   # main.py:266-267
+    feats2 = [f.float().cpu() for f in core._features(imgs[:2].to(dev))]
+    assert feats2[0].shape == (2, 512, 28, 28) and feats2[1].shape == (2, 1024, 14, 14)
+    assert np.abs(np.stack(rows) - restated.embed(feats2, 3, 1, 1024, 1024).numpy()).max() <= 5e-5
+    # main.py:266-267: batch_size = 1 loop, list of per-patch numpy rows -> torch.tensor(Z)
+    Zs, Zws = [], []
+    for i in range(5):
+        Zs.append(torch.from_numpy(np.stack(core._embed(imgs[i:i + 1], "unsupervised"))))
+        Zws.append(restated.embed([f.float().cpu() for f in core._features(imgs[i:i + 1].to(dev))], 3, 1, 1024, 1024))
+    Z = torch.stack(Zs)
+    Zw = torch.cat(Zws)
+    assert (Z.reshape(-1, 1024) - Zw).abs().max().item() <= 5e-5
     alpha = utils.Matrix_Alpha_Unsupervised(1.0, 1, Z, dev)
     assert alpha.dtype == torch.float64 and alpha.shape == (5, 784)
     want = restated.matrix_alpha_unsupervised(1.0, Zw.reshape(5, 784, 1024))
