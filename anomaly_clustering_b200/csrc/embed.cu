@@ -184,6 +184,27 @@ __device__ __forceinline__ void store_out(const EmbedParams& p, long long row, i
   }
 }
 
+
+// Warp-collective: mean / rstd of (image b, layer) from the statistics pre-pass partials
+// (biased variance, eps inside the sqrt -- nn.LayerNorm semantics, patchcore.py:384-385).
+__device__ __forceinline__ void warp_ln_params(const EmbedParams& p, const LayerDev& ly, int b, int layer, int lane, float& mu,
+                                               float& rstd) {
+  mu = 0.f;
+  rstd = 1.f;
+  if (!p.layernorm) return;
+  const double* st = p.stats + (((long long)b * p.L + layer) * kStatSplit) * 2;
+  double a = 0, q = 0;
+  for (int i = lane; i < kStatSplit; i += 32) { a += st[2 * i]; q += st[2 * i + 1]; }
+  a = warp_sum(a);
+  q = warp_sum(q);
+  const double n = (double)ly.C * ly.H * ly.W;
+  const double m = a / n;
+  double var = q / n - m * m;
+  if (var < 0) var = 0;
+  mu = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+}
+
 // MAXTAPS > 0: per-thread tap tables in registers.  MAXTAPS == 0: taps re-enumerated on the fly
 // (any pooling ratio / patch size; slow path).
 template <int MAXTAPS, bool RESAMPLE>
@@ -203,20 +224,8 @@ __global__ void __launch_bounds__(kThreads) embed_kernel(EmbedParams p, const Ch
 
   // ---- LayerNorm statistics of (image b, layer) from the pre-pass partials
   if (warp == 0) {
-    float mu = 0.f, rstd = 1.f;
-    if (p.layernorm) {
-      const double* st = p.stats + (((long long)b * p.L + ck.layer) * kStatSplit) * 2;
-      double a = 0, q = 0;
-      for (int i = lane; i < kStatSplit; i += 32) { a += st[2 * i]; q += st[2 * i + 1]; }
-      a = warp_sum(a);
-      q = warp_sum(q);
-      const double n = (double)ly.C * ly.H * ly.W;
-      const double m = a / n;
-      double var = q / n - m * m;
-      if (var < 0) var = 0;
-      mu = (float)m;
-      rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-    }
+    float mu, rstd;
+    warp_ln_params(p, ly, b, ck.layer, lane, mu, rstd);
     if (lane == 0) { s_mu = mu; s_rstd = rstd; }
   }
 
@@ -363,6 +372,56 @@ __global__ void __launch_bounds__(kThreads) embed_kernel(EmbedParams p, const Ch
 }
 
 
+
+// Writes NOUT consecutive outputs of one patch row: fp32 Z (16-byte vectors when aligned) and the
+// tensor-core operand copies hi = round(z), lo = round(z - hi).
+template <typename T, int NOUT>
+__device__ __forceinline__ void store_operand(void* Zhi, void* Zlo, long long idx, bool vec, const float (&out)[NOUT]) {
+  __align__(16) T h[NOUT];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) h[o] = to_op<T>(out[o]);
+  T* ph = reinterpret_cast<T*>(Zhi) + idx;
+  if (vec) {
+#pragma unroll
+    for (int o = 0; o + 8 <= NOUT; o += 8) *reinterpret_cast<uint4*>(ph + o) = *reinterpret_cast<const uint4*>(&h[o]);
+  } else {
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) ph[o] = h[o];
+  }
+  if (Zlo) {
+    __align__(16) T l[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) l[o] = to_op<T>(out[o] - op_to_float(h[o]));
+    T* pl = reinterpret_cast<T*>(Zlo) + idx;
+    if (vec) {
+#pragma unroll
+      for (int o = 0; o + 8 <= NOUT; o += 8) *reinterpret_cast<uint4*>(pl + o) = *reinterpret_cast<const uint4*>(&l[o]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) pl[o] = l[o];
+    }
+  }
+}
+
+template <int NOUT>
+__device__ __forceinline__ void store_outputs(const EmbedParams& p, long long idx, int t_base, const float (&out)[NOUT]) {
+  if (p.Z) {
+    if (NOUT % 4 == 0 && ((p.ldz | t_base) & 3) == 0) {
+#pragma unroll
+      for (int o = 0; o + 4 <= NOUT; o += 4)
+        *reinterpret_cast<float4*>(p.Z + idx + o) = make_float4(out[o], out[o + 1], out[o + 2], out[o + 3]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) p.Z[idx + o] = out[o];
+    }
+  }
+  if (p.Zhi) {
+    const bool vec = (NOUT % 8 == 0) && (((p.ldz | t_base) & 7) == 0);
+    if (p.op_dtype == AC_DT_F16) store_operand<__half, NOUT>(p.Zhi, p.Zlo, idx, vec, out);
+    else store_operand<__nv_bfloat16, NOUT>(p.Zhi, p.Zlo, idx, vec, out);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fast path for channel-contiguous layers (ViT tokens, channels_last maps) on the layer-0 grid,
 // stride 1: "periodic sliding window".  With 9C/Dp = A/B in lowest terms (A a multiple of K*K),
@@ -384,20 +443,8 @@ __global__ void __launch_bounds__(kThreads) embed_periodic_kernel(EmbedParams p,
   const int xa = xseg * p.xseg_len, xb = min(p.w0, xa + p.xseg_len);
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < 32) {
-    float mu = 0.f, rstd = 1.f;
-    if (p.layernorm) {
-      const double* st = p.stats + (((long long)b * p.L + layer) * kStatSplit) * 2;
-      double a = 0, q = 0;
-      for (int i = lane; i < kStatSplit; i += 32) { a += st[2 * i]; q += st[2 * i + 1]; }
-      a = warp_sum(a);
-      q = warp_sum(q);
-      const double n = (double)ly.C * ly.H * ly.W;
-      const double m = a / n;
-      double var = q / n - m * m;
-      if (var < 0) var = 0;
-      mu = (float)m;
-      rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-    }
+    float mu, rstd;
+    warp_ln_params(p, ly, b, layer, lane, mu, rstd);
     if (lane == 0) { s_mu = mu; s_rstd = rstd; }
   }
   __syncthreads();
@@ -465,53 +512,7 @@ __global__ void __launch_bounds__(kThreads) embed_periodic_kernel(EmbedParams p,
       }
       out[o] = (R == 1) ? acc_o : acc_o * (1.0f / (float)R);
     }
-    const long long idx = (row0 + x) * p.ldz + t0;
-    if (p.Z) {
-      if (NOUT % 4 == 0 && ((p.ldz | t_base) & 3) == 0) {
-#pragma unroll
-        for (int o = 0; o < NOUT; o += 4) *reinterpret_cast<float4*>(p.Z + idx + o) = make_float4(out[o], out[o + 1], out[o + 2], out[o + 3]);
-      } else {
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) p.Z[idx + o] = out[o];
-      }
-    }
-    if (p.Zhi) {
-      if (p.op_dtype == AC_DT_F16) {
-        __align__(16) __half h[NOUT];
-        __align__(16) __half l[NOUT];
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) { h[o] = __float2half_rn(out[o]); l[o] = __float2half_rn(out[o] - __half2float(h[o])); }
-        __half* ph = reinterpret_cast<__half*>(p.Zhi) + idx;
-        __half* pl = p.Zlo ? reinterpret_cast<__half*>(p.Zlo) + idx : nullptr;
-        if (NOUT % 8 == 0 && ((p.ldz | t_base) & 7) == 0) {
-#pragma unroll
-          for (int o = 0; o < NOUT; o += 8) {
-            *reinterpret_cast<uint4*>(ph + o) = *reinterpret_cast<const uint4*>(&h[o]);
-            if (pl) *reinterpret_cast<uint4*>(pl + o) = *reinterpret_cast<const uint4*>(&l[o]);
-          }
-        } else {
-#pragma unroll
-          for (int o = 0; o < NOUT; ++o) { ph[o] = h[o]; if (pl) pl[o] = l[o]; }
-        }
-      } else {
-        __align__(16) __nv_bfloat16 h[NOUT];
-        __align__(16) __nv_bfloat16 l[NOUT];
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) { h[o] = __float2bfloat16_rn(out[o]); l[o] = __float2bfloat16_rn(out[o] - __bfloat162float(h[o])); }
-        __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(p.Zhi) + idx;
-        __nv_bfloat16* pl = p.Zlo ? reinterpret_cast<__nv_bfloat16*>(p.Zlo) + idx : nullptr;
-        if (NOUT % 8 == 0 && ((p.ldz | t_base) & 7) == 0) {
-#pragma unroll
-          for (int o = 0; o < NOUT; o += 8) {
-            *reinterpret_cast<uint4*>(ph + o) = *reinterpret_cast<const uint4*>(&h[o]);
-            if (pl) *reinterpret_cast<uint4*>(pl + o) = *reinterpret_cast<const uint4*>(&l[o]);
-          }
-        } else {
-#pragma unroll
-          for (int o = 0; o < NOUT; ++o) { ph[o] = h[o]; if (pl) pl[o] = l[o]; }
-        }
-      }
-    }
+    store_outputs<NOUT>(p, (row0 + x) * p.ldz + t0, t_base, out);
   }
 }
 
@@ -585,20 +586,8 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_tma_kernel(EmbedParams
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    float mu = 0.f, rstd = 1.f;
-    if (p.layernorm) {
-      const double* st = p.stats + (((long long)b * p.L + layer) * kStatSplit) * 2;
-      double a = 0, q = 0;
-      for (int i = lane; i < kStatSplit; i += 32) { a += st[2 * i]; q += st[2 * i + 1]; }
-      a = warp_sum(a);
-      q = warp_sum(q);
-      const double n = (double)ly.C * ly.H * ly.W;
-      const double m = a / n;
-      double var = q / n - m * m;
-      if (var < 0) var = 0;
-      mu = (float)m;
-      rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-    }
+    float mu, rstd;
+    warp_ln_params(p, ly, b, layer, lane, mu, rstd);
     if (lane == 0) { s_mu = mu; s_rstd = rstd; }
   }
   __syncthreads();
@@ -712,71 +701,7 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_tma_kernel(EmbedParams
       }
       out[o] = (R == 1) ? acc_o : acc_o * (1.0f / (float)R);
     }
-    const long long idx = (row0 + x) * p.ldz + t0;
-    if (p.Z) {
-      if (NOUT % 4 == 0 && ((p.ldz | t_base) & 3) == 0) {
-#pragma unroll
-        for (int o = 0; o < NOUT; o += 4) *reinterpret_cast<float4*>(p.Z + idx + o) = make_float4(out[o], out[o + 1], out[o + 2], out[o + 3]);
-      } else {
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) p.Z[idx + o] = out[o];
-      }
-    }
-    if (p.Zhi) {
-      if (p.op_dtype == AC_DT_F16) {
-        __align__(16) __half h[NOUT];
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) h[o] = __float2half_rn(out[o]);
-        __half* ph_ = reinterpret_cast<__half*>(p.Zhi) + idx;
-        const bool vec = (NOUT % 8 == 0) && (((p.ldz | t_base) & 7) == 0);
-        if (vec) {
-#pragma unroll
-          for (int o = 0; o < NOUT; o += 8) *reinterpret_cast<uint4*>(ph_ + o) = *reinterpret_cast<const uint4*>(&h[o]);
-        } else {
-#pragma unroll
-          for (int o = 0; o < NOUT; ++o) ph_[o] = h[o];
-        }
-        if (p.Zlo) {
-          __align__(16) __half l[NOUT];
-#pragma unroll
-          for (int o = 0; o < NOUT; ++o) l[o] = __float2half_rn(out[o] - __half2float(h[o]));
-          __half* pl_ = reinterpret_cast<__half*>(p.Zlo) + idx;
-          if (vec) {
-#pragma unroll
-            for (int o = 0; o < NOUT; o += 8) *reinterpret_cast<uint4*>(pl_ + o) = *reinterpret_cast<const uint4*>(&l[o]);
-          } else {
-#pragma unroll
-            for (int o = 0; o < NOUT; ++o) pl_[o] = l[o];
-          }
-        }
-      } else {
-        __align__(16) __nv_bfloat16 h[NOUT];
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) h[o] = __float2bfloat16_rn(out[o]);
-        __nv_bfloat16* ph_ = reinterpret_cast<__nv_bfloat16*>(p.Zhi) + idx;
-        const bool vec = (NOUT % 8 == 0) && (((p.ldz | t_base) & 7) == 0);
-        if (vec) {
-#pragma unroll
-          for (int o = 0; o < NOUT; o += 8) *reinterpret_cast<uint4*>(ph_ + o) = *reinterpret_cast<const uint4*>(&h[o]);
-        } else {
-#pragma unroll
-          for (int o = 0; o < NOUT; ++o) ph_[o] = h[o];
-        }
-        if (p.Zlo) {
-          __align__(16) __nv_bfloat16 l[NOUT];
-#pragma unroll
-          for (int o = 0; o < NOUT; ++o) l[o] = __float2bfloat16_rn(out[o] - __bfloat162float(h[o]));
-          __nv_bfloat16* pl_ = reinterpret_cast<__nv_bfloat16*>(p.Zlo) + idx;
-          if (vec) {
-#pragma unroll
-            for (int o = 0; o < NOUT; o += 8) *reinterpret_cast<uint4*>(pl_ + o) = *reinterpret_cast<const uint4*>(&l[o]);
-          } else {
-#pragma unroll
-            for (int o = 0; o < NOUT; ++o) pl_[o] = l[o];
-          }
-        }
-      }
-    }
+    store_outputs<NOUT>(p, (row0 + x) * p.ldz + t0, t_base, out);
   };
   for (int j0 = 0; j0 < ncols; j0 += 3) {
     step(std::integral_constant<int, 1>{}, j0);

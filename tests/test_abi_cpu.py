@@ -69,3 +69,25 @@ def test_sass_is_blackwell_native(lib_path):
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in sass, mnemonic
+
+
+def test_argument_validation_needs_no_gpu(lib_path):
+    """Null pointers / bad sizes are rejected before any CUDA call; valid-looking calls fail loudly
+    (AC_ERR_CUDA or AC_ERR_DEVICE) on a machine without a B200 -- never a silent CPU path."""
+    import torch
+
+    from anomaly_clustering_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.ac_pairwise_l2(None, 4, 8, None, None) == _lib.AC_ERR_INVALID
+    assert lib.ac_weighted_embed(None, None, 1, 1, 1, None, None) == _lib.AC_ERR_INVALID
+    assert lib.ac_reduce_weights(None, 1, 1, 1, None, 0, None, None) == _lib.AC_ERR_INVALID
+    assert lib.ac_min_dist(None, None, None, 1, None, None, None, 1, 1, 8, 0, None, None, 0, None) == _lib.AC_ERR_INVALID
+    assert lib.ac_embed(None, 1, 1, 3, 1, 8, 8, 1, 1e-5, None, None, None, 0, None, 0, None) == _lib.AC_ERR_INVALID
+    assert lib.ac_debug_set(0, 7) == _lib.AC_ERR_INVALID
+    if not torch.cuda.is_available():
+        buf = (ctypes.c_float * 64)()
+        rc = lib.ac_pairwise_l2(ctypes.cast(buf, ctypes.c_void_p), 4, 8, ctypes.cast(buf, ctypes.c_void_p), None)
+        assert rc in (_lib.AC_ERR_CUDA, _lib.AC_ERR_DEVICE)
+        with pytest.raises(_lib.AcError):
+            _lib.check(rc, "ac_pairwise_l2")
