@@ -48,7 +48,7 @@ SIGNATURES = {
     "ac_strerror": (c_char_p, [c_int]),
     "ac_device_ok": (c_int, [c_int]),
     "ac_last_cuda_error": (c_int, []),
-    "ac_embed_workspace_bytes": (c_size_t, [c_int, c_int, c_int64, c_int, c_int]),
+    "ac_embed_workspace_bytes": (c_size_t, [POINTER(AcLayer), c_int, c_int, c_int, c_int, c_int, c_int]),
     "ac_embed": (
         c_int,
         [POINTER(AcLayer), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int,

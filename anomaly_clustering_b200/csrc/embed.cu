@@ -710,6 +710,77 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_tma_kernel(EmbedParams
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Layout / grid adapters that let every layer take the periodic fast path:
+//  * nchw_to_nhwc_kernel: CNN maps [B,C,H,W] -> channel-contiguous scratch (32x32 smem tile transpose).
+//  * upsample_store_kernel: a layer whose patch grid differs from layer 0 is pooled at ITS OWN grid into a
+//    small scratch and then resampled; the reference resamples the unfolded planes and pools afterwards
+//    (patchcore.py:398-421), but both maps are linear and act on different axes (positions vs. the flat
+//    patch vector), so they commute -- same bilinear weights (align_corners=False), 1/9 of the gathers.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(LayerDev ly, int b0, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int HW = ly.H * ly.W;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const float* src = ly.ptr + (long long)(b0 + b) * ly.sb;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, pos = p0 + tx;
+    float v = 0.f;
+    if (c < ly.C && pos < HW) {
+      const int y = pos / ly.W, x = pos - y * ly.W;
+      v = __ldg(src + (long long)c * ly.sc + (long long)y * ly.sh + (long long)x * ly.sw);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  float* dst = out + (long long)b * HW * ly.C;
+  for (int r = ty; r < 32; r += 8) {
+    const int pos = p0 + r, c = c0 + tx;
+    if (c < ly.C && pos < HW) dst[(long long)pos * ly.C + c] = tile[tx][r];
+  }
+}
+
+// coarse [B, gh*gw, ncols] fp32 -> Z / Zhi / Zlo columns [t_base, t_base + ncols) on the layer-0 grid
+__global__ void __launch_bounds__(256) upsample_store_kernel(EmbedParams p, const float* __restrict__ coarse, int gh, int gw, int ncols,
+                                                             int t_base) {
+  const int cpr = (ncols + 3) / 4;                       // 4-column groups per row
+  const long long rows = (long long)p.B * p.h0 * p.w0;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < rows * cpr; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / cpr;
+    const int c4 = (int)(e - row * cpr) * 4;
+    const int x = (int)(row % p.w0);
+    const int y = (int)((row / p.w0) % p.h0);
+    const int b = (int)(row / ((long long)p.w0 * p.h0));
+    int y0, y1, x0, x1;
+    float ly1, lx1;
+    bilinear_src(y, gh, p.h0, y0, y1, ly1);
+    bilinear_src(x, gw, p.w0, x0, x1, lx1);
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float* base = coarse + (long long)b * gh * gw * ncols;
+    const float* r00 = base + ((long long)y0 * gw + x0) * ncols;
+    const float* r01 = base + ((long long)y0 * gw + x1) * ncols;
+    const float* r10 = base + ((long long)y1 * gw + x0) * ncols;
+    const float* r11 = base + ((long long)y1 * gw + x1) * ncols;
+    float out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = min(c4 + i, ncols - 1);
+      out[i] = ly0 * (lx0 * __ldg(r00 + c) + lx1 * __ldg(r01 + c)) + ly1 * (lx0 * __ldg(r10 + c) + lx1 * __ldg(r11 + c));
+    }
+    const long long grow = (long long)p.b0 * p.h0 * p.w0 + row;
+    if (c4 + 4 <= ncols) {
+      store_outputs<4>(p, grow * p.ldz + t_base + c4, t_base | c4, out);
+    } else {
+      for (int i = 0; c4 + i < ncols; ++i) {
+        const float o1[1] = {out[i]};
+        store_outputs<1>(p, grow * p.ldz + t_base + c4 + i, 1, o1);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // standalone compat kernels
 __global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int H, int W, int k, int s, int pad,
@@ -955,15 +1026,15 @@ static int dispatch_taps(const EmbedParams& p, const Plan& plan, int l, const Ch
 }
 
 // ---- periodic fast path: eligibility and dispatch
-struct Periodic { int ok, A, B, R, nperiods, t_base; };
+struct Periodic { int ok, A, B, R, nperiods, t_base, transpose, upsample, ncols; };
 
 static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
 static Periodic periodic_of(const Plan& plan, int l) {
-  Periodic pr = {0, 0, 0, 0, 0, 0};
+  Periodic pr = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   const EmbedParams& p = plan.p;
   const LayerDev& ly = p.layers[l];
-  if (!plan.fused || ly.sc != 1 || ly.resample || p.s != 1 || p.k != 3) return pr;
+  if (!plan.fused || p.s != 1 || p.k != 3) return pr;
   if (p.agg_in % p.agg_out != 0) return pr;
   const int R = p.agg_in / p.agg_out;
   if (p.Dp % R != 0) return pr;
@@ -976,6 +1047,9 @@ static Periodic periodic_of(const Plan& plan, int l) {
     a *= f; b *= f;
   }
   pr.A = a; pr.B = b; pr.R = R; pr.nperiods = p.Dp / b; pr.t_base = l * (p.Dp / R);
+  pr.transpose = (ly.sc != 1);      // CNN layout: go through a channel-contiguous scratch copy
+  pr.upsample = ly.resample;        // pool at the layer's own grid, then resample
+  pr.ncols = p.Dp / R;
   pr.ok = 1;
   return pr;
 }
@@ -1078,13 +1152,40 @@ static bool aggregator_fusable(int L, int Dp, int D) {
   return true;
 }
 
-extern "C" size_t ac_embed_workspace_bytes(int L, int B, int64_t P, int Dp, int D) {
-  if (L < 1 || B < 1 || P < 1 || Dp < 1 || D < 1) return 0;
+// scratch needed by the layout / grid adapters of the fast path (upper bound: assumes every layer uses them)
+static size_t adapter_bytes(const ac_layer_t* layers, int L, int B, int k, int s, int Dp, int D, size_t* per_layer_t, size_t* per_layer_c) {
+  size_t total = 0;
+  const int pad = (k - 1) / 2;
+  const int R = std::max(1, (L * Dp) / std::max(1, D));
+  for (int l = 0; l < L; ++l) {
+    const size_t tb = align256((size_t)B * layers[l].C * layers[l].H * layers[l].W * sizeof(float));
+    const int gh = (layers[l].H + 2 * pad - (k - 1) - 1) / s + 1, gw = (layers[l].W + 2 * pad - (k - 1) - 1) / s + 1;
+    const size_t cb = align256((size_t)B * std::max(1, gh) * std::max(1, gw) * (size_t)(Dp / R + 4) * sizeof(float));
+    if (per_layer_t) per_layer_t[l] = tb;
+    if (per_layer_c) per_layer_c[l] = cb;
+    total += tb + cb;
+  }
+  return total;
+}
+
+extern "C" size_t ac_embed_workspace_bytes(const ac_layer_t* layers, int L, int B, int patchsize, int stride, int Dp, int D) {
+  if (!layers || L < 1 || L > kMaxLayers || B < 1 || patchsize < 1 || stride < 1 || Dp < 1 || D < 1) return 0;
+  const int pad = (patchsize - 1) / 2;
+  const long long P = (long long)((layers[0].H + 2 * pad - (patchsize - 1) - 1) / stride + 1) *
+                      ((layers[0].W + 2 * pad - (patchsize - 1) - 1) / stride + 1);
+  if (P < 1) return 0;
   size_t stats = align256((size_t)B * L * kStatSplit * 2 * sizeof(double));
   size_t chunks = align256(((size_t)L * Dp / 32 + (size_t)D / 32 + 2 * L + 16) * sizeof(ChunkDesc));
   // the [B*P, L*Dp] concat scratch exists only when an Aggregator window straddles two layers
   size_t concat = aggregator_fusable(L, Dp, D) ? 0 : align256((size_t)B * P * (size_t)L * Dp * sizeof(float));
-  return stats + chunks + concat;
+  // channel-contiguous copies of CNN-layout maps + coarse pooled tiles of resampled layers (fast path)
+  bool any_adapter = false;
+  for (int l = 0; l < L; ++l) {
+    const int gh = (layers[l].H + 2 * pad - (patchsize - 1) - 1) / stride + 1, gw = (layers[l].W + 2 * pad - (patchsize - 1) - 1) / stride + 1;
+    if (layers[l].sc != 1 || (long long)gh * gw != P) any_adapter = true;
+  }
+  size_t adapters = any_adapter ? adapter_bytes(layers, L, B, patchsize, stride, Dp, D, nullptr, nullptr) : 0;
+  return stats + chunks + concat + adapters;
 }
 
 extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, int stride, int Dp, int D, int layernorm,
@@ -1121,11 +1222,25 @@ extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, i
   float* dconcat = (float*)(w8 + stats_b + chunks_b);
 
   Periodic pr[kMaxLayers];
-  bool need_chunks = false;
+  bool need_chunks = false, any_adapter = false;
   for (int l = 0; l < L; ++l) {
     pr[l] = periodic_of(plan, l);
     if (pr[l].ok && (!periodic_instantiated(pr[l]) || g_embed_variant == 2)) pr[l].ok = 0;
     if (!pr[l].ok && plan.pl[l].nchunks > 0) need_chunks = true;
+    if (pr[l].ok && (pr[l].transpose || pr[l].upsample)) any_adapter = true;
+  }
+  // scratch of the layout / grid adapters (only carved when a fast-path layer needs one)
+  size_t tb[kMaxLayers], cb[kMaxLayers];
+  float* tbuf[kMaxLayers] = {nullptr};
+  float* cbuf[kMaxLayers] = {nullptr};
+  if (any_adapter) {
+    const size_t ad = adapter_bytes(layers, L, B, patchsize, stride, Dp, D, tb, cb);
+    if (stats_b + chunks_b + concat_b + ad > ws_bytes) return AC_ERR_WORKSPACE;
+    char* cur = w8 + stats_b + chunks_b + concat_b;
+    for (int l = 0; l < L; ++l) {
+      tbuf[l] = (float*)cur; cur += tb[l];
+      cbuf[l] = (float*)cur; cur += cb[l];
+    }
   }
   if (need_chunks)
     AC_CUDA(cudaMemcpyAsync(dchunks, plan.chunks.data(), plan.chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, st));
@@ -1153,9 +1268,37 @@ extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, i
     }
     for (int l = 0; l < L; ++l) {
       if (plan.pl[l].nchunks == 0) continue;
-      if (pr[l].ok) rc = launch_periodic(p, pr[l], l, num_sms, st);
-      else rc = p.layers[l].resample ? dispatch_taps<true>(p, plan, l, dchunks, st) : dispatch_taps<false>(p, plan, l, dchunks, st);
+      if (!pr[l].ok) {
+        rc = p.layers[l].resample ? dispatch_taps<true>(p, plan, l, dchunks, st) : dispatch_taps<false>(p, plan, l, dchunks, st);
+        if (rc) return rc;
+        continue;
+      }
+      EmbedParams q = p;
+      Periodic prl = pr[l];
+      LayerDev& ly = q.layers[l];
+      if (prl.transpose) {
+        // CNN layout -> channel-contiguous scratch [B, H*W, C]
+        dim3 tg(ceil_div(ly.H * ly.W, 32), ceil_div(ly.C, 32), q.B);
+        nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(p.layers[l], q.b0, tbuf[l]);
+        AC_LAUNCH_CHECK();
+        ly.ptr = tbuf[l] - (long long)q.b0 * ly.C * ly.H * ly.W;   // kernels index images as b0 + blockIdx.z
+        ly.sb = (long long)ly.C * ly.H * ly.W; ly.sc = 1; ly.sh = (long long)ly.W * ly.C; ly.sw = ly.C;
+      }
+      if (prl.upsample) {
+        // pool at the layer's own patch grid into scratch [B, gh*gw, ncols], resample afterwards
+        q.h0 = ly.gh; q.w0 = ly.gw;
+        q.Z = cbuf[l] - (long long)q.b0 * ly.gh * ly.gw * prl.ncols;
+        q.Zhi = nullptr; q.Zlo = nullptr; q.op_dtype = 0; q.ldz = prl.ncols;
+        prl.t_base = 0;
+      }
+      rc = launch_periodic(q, prl, l, num_sms, st);
       if (rc) return rc;
+      if (prl.upsample) {
+        const long long groups = (long long)p.B * p.h0 * p.w0 * ((prl.ncols + 3) / 4);
+        const int blocks = (int)std::min<long long>((groups + 255) / 256, (long long)num_sms * 32);
+        upsample_store_kernel<<<blocks, 256, 0, st>>>(p, cbuf[l], ly.gh, ly.gw, prl.ncols, pr[l].t_base);
+        AC_LAUNCH_CHECK();
+      }
     }
   }
   if (!plan.fused) {

@@ -105,8 +105,7 @@ def embed(
         hi = out_hi if out_hi is not None else torch.empty(rows, target_dim, dtype=tdt, device=dev)
         if want_lo:
             lo = out_lo if out_lo is not None else torch.empty(rows, target_dim, dtype=tdt, device=dev)
-    ws_bytes = lib.ac_embed_workspace_bytes(L, B, h * w, pretrain_dim, target_dim)
-    # the concat scratch is only touched when the Aggregator cannot be fused; allocate lazily sized
+    ws_bytes = lib.ac_embed_workspace_bytes(arr, L, B, patchsize, stride, pretrain_dim, target_dim)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     rc = lib.ac_embed(arr, L, B, patchsize, stride, pretrain_dim, target_dim, int(layernorm), float(eps), _ptr(Z), _ptr(hi),
                       _ptr(lo), op_code, _ptr(ws), ws_bytes, _stream())

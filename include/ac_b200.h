@@ -80,8 +80,10 @@ int ac_last_cuda_error(void);
  *   Zhi, Zlo    : [B*P, D] op_dtype (AC_DT_F16/AC_DT_BF16) or NULL: hi = round(Z), lo = round(Z-hi),
  *                 the tensor-core operands of ac_min_dist
  *   layernorm   : 1 = AnomalyClusteringCore._embed, 0 = PatchCore._embed (patchcore.py:92-146)
- * Workspace: ac_embed_workspace_bytes(L, B, P, Dp, D). */
-size_t ac_embed_workspace_bytes(int L, int B, int64_t P, int Dp, int D);
+ * Workspace: ac_embed_workspace_bytes(layers_host, L, B, patchsize, stride, Dp, D) (statistics partials,
+ * chunk table, and -- only for CNN-layout or resampled layers -- channel-contiguous / coarse-grid scratch). */
+size_t ac_embed_workspace_bytes(const ac_layer_t* layers_host, int L, int B, int patchsize, int stride, int Dp,
+                                int D);
 int ac_embed(const ac_layer_t* layers_host, int L, int B, int patchsize, int stride, int Dp, int D,
              int layernorm, float eps, float* Z, void* Zhi, void* Zlo, int op_dtype, void* ws,
              size_t ws_bytes, ac_stream_t stream);

@@ -41,8 +41,10 @@ def test_binding_covers_header(lib_path):
     assert lib.ac_version() >= 100
     assert lib.ac_strerror(-3).decode().startswith("device is not sm_100")
     # workspace sizing is host-only arithmetic
-    assert lib.ac_embed_workspace_bytes(2, 4, 784, 2048, 4096) < (1 << 20)          # fused aggregator: no concat scratch
-    assert lib.ac_embed_workspace_bytes(3, 3, 100, 100, 77) > 3 * 100 * 300 * 4      # straddling windows need it
+    tok = (_lib.AcLayer * 2)(_lib.AcLayer(0, 768, 28, 28, 785 * 768, 1, 28 * 768, 768), _lib.AcLayer(0, 768, 28, 28, 785 * 768, 1, 28 * 768, 768))
+    assert lib.ac_embed_workspace_bytes(tok, 2, 4, 3, 1, 2048, 4096) < (1 << 20)    # token layout, fused aggregator: no scratch
+    cnn = (_lib.AcLayer * 3)(*[_lib.AcLayer(0, 40, 10, 10, 4000, 100, 10, 1)] * 3)
+    assert lib.ac_embed_workspace_bytes(cnn, 3, 3, 3, 1, 100, 77) > 3 * 100 * 300 * 4   # straddling Aggregator windows need the concat
     assert lib.ac_min_dist_workspace_bytes(1000, 10, 784, 4096, 0) >= 256
 
 
