@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -162,7 +162,7 @@ def run_reference_arm(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
@@ -324,6 +324,11 @@ def main():
                 d2h_bytes = sum(o.numel() * o.element_size() for o in outs)
             return d2h_bytes
 
+        # raw pinned-host -> device copy rate of this box (explains the gap between `value` and `e2e`)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        issue_copy(0); torch.cuda.synchronize()
+        c0.record(copy_stream); issue_copy(0); c1.record(copy_stream); torch.cuda.synchronize()
+        h2d_gbps = h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
         d2h = e2e_run(3)
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -337,7 +342,8 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
             dist.all_reduce(tb, op=dist.ReduceOp.SUM)
         e2e = {"value": n_img * args.steps / (float(te.item()) * 1e-3), "unit": "images/s",
-               "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item())}
+               "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()),
+               "h2d_GBps_measured_per_gpu": h2d_gbps}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1)
     cpu_baseline = None
