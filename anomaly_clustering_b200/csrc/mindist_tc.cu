@@ -54,8 +54,10 @@ struct __align__(64) TcParams {
   int sym;                   // 0 = every (query block, bank image) unit; 1 = only pairs owned by the query image
   int q_img0;                // global image index of query row 0 (query slice of a sharded run)
   int KU;                    // units per query block in sym mode
+  int l2_hint;               // 1: operand loads carry an L2 evict_last policy
   unsigned int* colmin;      // [nq_img, nb_img*P] squared distances (fp32 bits), atomicMin target
-  const int2* units;         // sym mode: explicit (query block, bank image) list in raster order
+  const int2* units;         // sym mode: explicit (query block, bank image) list in raster order (device-built)
+  const long long* n_units;  // sym mode: length of that list (device memory)
 };
 
 // Ownership of the unordered pair {i, j} of N images: the image that sees the other one within the
@@ -128,6 +130,29 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// same as tma_load_2d with an L2 eviction-priority hint: the operand working set (A group + a few bank
+// images) must stay L2-resident against unrelated traffic (e.g. a concurrent H2D copy streaming through L2)
+template <int G>
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t pol) {
+  if (G == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+  }
 }
 
 template <int G>
@@ -276,6 +301,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
   const bool leader = (rank == 0);
   const long long worker = (G == 2) ? (blockIdx.x >> 1) : blockIdx.x;
   const long long nworkers = (G == 2) ? (gridDim.x >> 1) : gridDim.x;
+  const long long total_units = p.sym ? __ldg(p.n_units) : p.total_units;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -301,8 +327,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
     // ================================================================ TMA producer
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
+      const uint64_t pol = l2_policy_evict_last();
       const uint32_t full0 = (G == 2) ? mapa_rank(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
-      for (long long u = worker; u < p.total_units; u += nworkers) {
+      for (long long u = worker; u < total_units; u += nworkers) {
         int mb, img;
         if (!decode_unit<G>(p, u, mb, img)) continue;
         const int arow = mb * (kTileM * G) + (int)rank * kTileM;
@@ -319,8 +346,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
               if (leader) mbar_expect_tx(smem_u32(&full_bar[stage]), (kABytes + bbytes) * G);
               const uint32_t fb = full0 + stage * 8;
               uint8_t* sa = smem + stage * kStageBytes;
-              tma_load_2d<G>(smem_u32(sa), ma, fb, kb * kBlockK, arow);
-              tma_load_2d<G>(smem_u32(sa + kABytes), mbp, fb, kb * kBlockK, brow);
+              if (p.l2_hint) {
+                tma_load_2d_hint<G>(smem_u32(sa), ma, fb, kb * kBlockK, arow, pol);
+                tma_load_2d_hint<G>(smem_u32(sa + kABytes), mbp, fb, kb * kBlockK, brow, pol);
+              } else {
+                tma_load_2d<G>(smem_u32(sa), ma, fb, kb * kBlockK, arow);
+                tma_load_2d<G>(smem_u32(sa + kABytes), mbp, fb, kb * kBlockK, brow);
+              }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -332,7 +364,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
     if (leader && elect_one()) {
       uint32_t stage = 0, phase = 0;
       uint32_t tile_ctr = 0;
-      for (long long u = worker; u < p.total_units; u += nworkers) {
+      for (long long u = worker; u < total_units; u += nworkers) {
         int mb_, img_;
         if (!decode_unit<G>(p, u, mb_, img_)) continue;
         for (int t = 0; t < p.nt; ++t, ++tile_ctr) {
@@ -367,7 +399,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
     const int eidx = threadIdx.x - 64;            // 0..127
     const uint32_t tempty0 = (G == 2) ? mapa_rank(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
     uint32_t tile_ctr = 0;
-    for (long long u = worker; u < p.total_units; u += nworkers) {
+    for (long long u = worker; u < total_units; u += nworkers) {
       int mb, img;
       if (!decode_unit<G>(p, u, mb, img)) continue;
       const long long row = (long long)mb * (kTileM * G) + rank * kTileM + et;
@@ -468,6 +500,71 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
   if (warp == 2) tmem_dealloc<G>(tmem_base, kTmemCols);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Device-side construction of the symmetric raster list.  (A host-built list needs an H2D copy, and
+// copy-engine work queues behind any large transfer the application has in flight -- measured: +9 ms
+// per launch while the next category's features were being uploaded.)  Single CTA: row r = (group, k)
+// of the raster, count its active query blocks, block-wide exclusive scan, then emit.
+__device__ __forceinline__ bool unit_has_work(const TcParams& p, int G, int mb, int img) {
+  const long long rows_per_mb = (long long)kTileM * G;
+  const long long r0 = (long long)mb * rows_per_mb, r1 = min(p.Mq, r0 + rows_per_mb) - 1;
+  const int i0 = p.q_img0 + (int)(r0 / p.P), i1 = p.q_img0 + (int)(r1 / p.P);
+  for (int i = i0; i <= i1; ++i)
+    if (pair_owned(i, img, p.nb_img)) return true;
+  return false;
+}
+
+__global__ void __launch_bounds__(1024) build_units_kernel(TcParams p, int G, int2* units, long long* n_units, int* err_flag,
+                                                           unsigned int* colmin, long long colmin_words) {
+  __shared__ long long s_scan[1024];
+  const int tid = threadIdx.x;
+  if (tid == 0 && err_flag) *err_flag = 0;
+  const int n_groups = (p.n_mblocks + p.GM - 1) / p.GM;
+  const long long rows = (long long)n_groups * p.KU;
+  const long long rows_per_mb = (long long)kTileM * G;
+  auto row_info = [&](long long r, int& mg, int& img, int& gm_cur) {
+    mg = (int)(r / p.KU);
+    const int k = (int)(r - (long long)mg * p.KU);
+    gm_cur = min(p.GM, p.n_mblocks - mg * p.GM);
+    const int ig = p.q_img0 + (int)(((long long)mg * p.GM * rows_per_mb) / p.P);
+    img = (ig + 1 + k) % p.nb_img;
+  };
+  // contiguous slice of rows per thread keeps the raster order after the scan
+  const long long per = (rows + blockDim.x - 1) / blockDim.x;
+  const long long ra = min(rows, (long long)tid * per), rb = min(rows, ra + per);
+  long long cnt = 0;
+  for (long long r = ra; r < rb; ++r) {
+    int mg, img, gm_cur;
+    row_info(r, mg, img, gm_cur);
+    for (int mi = 0; mi < gm_cur; ++mi) cnt += unit_has_work(p, G, mg * p.GM + mi, img) ? 1 : 0;
+  }
+  s_scan[tid] = cnt;
+  __syncthreads();
+  for (int off = 1; off < (int)blockDim.x; off <<= 1) {   // Hillis-Steele inclusive scan
+    const long long v = (tid >= off) ? s_scan[tid - off] : 0;
+    __syncthreads();
+    s_scan[tid] += v;
+    __syncthreads();
+  }
+  long long pos = s_scan[tid] - cnt;
+  if (tid == (int)blockDim.x - 1) *n_units = s_scan[tid];
+  for (long long r = ra; r < rb; ++r) {
+    int mg, img, gm_cur;
+    row_info(r, mg, img, gm_cur);
+    for (int mi = 0; mi < gm_cur; ++mi) {
+      const int mb = mg * p.GM + mi;
+      if (unit_has_work(p, G, mb, img)) units[pos++] = make_int2(mb, img);
+    }
+  }
+  (void)colmin; (void)colmin_words;
+}
+
+// grid-stride fill (SM-side replacement of cudaMemsetAsync: keeps the launch sequence off the copy engines)
+__global__ void fill_u32_kernel(unsigned int* __restrict__ dst, long long n, unsigned int v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = v;
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -509,6 +606,7 @@ static uint32_t make_idesc(int M, int N, bool bf16) {
 }
 
 static int g_tc_cta_group = 2;   // test hook (ac_debug_set): 1 = single-CTA MMAs, 2 = CTA pairs
+static int g_tc_l2hint = 0;  // debug knob 3
 static int g_tc_gm = 16;  // query blocks per raster group: 16 x 2 MB of A + the streaming bank images stay L2-resident (tuned on B200)
 
 template <int G, int kStages>
@@ -558,50 +656,24 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.nseg = x3 ? 3 : 1;
   prm.n_mblocks = (int)ceil_div64(Mq, (long long)kTileM * G);
   prm.GM = g_tc_gm;
+  prm.l2_hint = g_tc_l2hint;
   prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin; prm.units = nullptr;
   // bank images a raster group of GM query blocks can own: N/2 after each of the images it spans
   prm.KU = std::min(nb_img, nb_img / 2 + (int)(((long long)prm.GM * kTileM * G - 1) / P) + 1);
   prm.total_units = (long long)prm.n_mblocks * nb_img;
   if (sym) {
     // raster order: groups of GM query blocks; inside a group walk the bank images the group owns and,
-    // per bank image, every block of the group that owns the pair (blocks sharing a bank image run together)
-    std::vector<int2> units;
-    units.reserve((size_t)prm.n_mblocks * (nb_img / 2 + 2));
-    const long long rows_per_mb = (long long)kTileM * G;
-    for (int mg = 0; mg * prm.GM < prm.n_mblocks; ++mg) {
-      const int gm_cur = std::min(prm.GM, prm.n_mblocks - mg * prm.GM);
-      const int ig = q_img0 + (int)(((long long)mg * prm.GM * rows_per_mb) / P);
-      for (int k = 0; k < prm.KU; ++k) {
-        const int img = (ig + 1 + k) % nb_img;
-        for (int mi = 0; mi < gm_cur; ++mi) {
-          const int mb = mg * prm.GM + mi;
-          const long long r0 = (long long)mb * rows_per_mb, r1 = std::min<long long>(Mq, r0 + rows_per_mb) - 1;
-          const int i0 = q_img0 + (int)(r0 / P), i1 = q_img0 + (int)(r1 / P);
-          bool work = false;
-          for (int i = i0; i <= i1 && !work; ++i) work = pair_owned(i, img, nb_img);
-          if (work) units.push_back(make_int2(mb, img));
-        }
-      }
-    }
-    prm.total_units = (long long)units.size();
-    if (prm.total_units == 0) return AC_OK;
-    if (!unit_ws || unit_ws_bytes < units.size() * sizeof(int2)) return AC_ERR_WORKSPACE;
-    AC_CUDA(cudaMemcpyAsync(unit_ws, units.data(), units.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    prm.units = (const int2*)unit_ws;
-  }
-  prm.idesc_main = make_idesc(kTileM * G, wmain, bf16);
-  prm.idesc_last = make_idesc(kTileM * G, wlast, bf16);
-  const long long brows = (long long)nb_img * P;
-  int rc;
-  if ((rc = make_map(&prm.mapA[0], Qhi, Mq, D, kTileM, bf16))) return rc;
-  if ((rc = make_map(&prm.mapBmain[0], Bhi, brows, D, wmain / G, bf16))) return rc;
-  if ((rc = make_map(&prm.mapBlast[0], Bhi, brows, D, wlast / G, bf16))) return rc;
-  if (x3) {
-    if ((rc = make_map(&prm.mapA[1], Qlo, Mq, D, kTileM, bf16))) return rc;
-    if ((rc = make_map(&prm.mapBmain[1], Blo, brows, D, wmain / G, bf16))) return rc;
-    if ((rc = make_map(&prm.mapBlast[1], Blo, brows, D, wlast / G, bf16))) return rc;
-  } else {
-    prm.mapA[1] = prm.mapA[0]; prm.mapBmain[1] = prm.mapBmain[0]; prm.mapBlast[1] = prm.mapBlast[0];
+    // per bank image, every block of the group that owns the pair (blocks sharing a bank image run
+    // together).  Built on the device (build_units_kernel).
+    const long long max_units = (long long)prm.n_mblocks * prm.KU;
+    if (!unit_ws || unit_ws_bytes < 16 + (size_t)max_units * sizeof(int2)) return AC_ERR_WORKSPACE;
+    long long* d_n = (long long*)unit_ws;
+    int2* d_units = (int2*)((char*)unit_ws + 16);
+    build_units_kernel<<<1, 1024, 0, st>>>(prm, G, d_units, d_n, err_flag, nullptr, 0);
+    AC_LAUNCH_CHECK();
+    prm.units = d_units;
+    prm.n_units = d_n;
+    prm.total_units = max_units;   // upper bound (sizes the grid); the kernel reads the exact count
   }
   int dev = 0, num_sms = 0;
   AC_CUDA(cudaGetDevice(&dev));
@@ -622,6 +694,7 @@ extern "C" int ac_debug_set(int key, int value) {
   if (key == 2) return ac_debug_set_embed(value);
   if (key == 0 && (value == 1 || value == 2)) { g_tc_cta_group = value; return AC_OK; }
   if (key == 1 && value >= 1) { g_tc_gm = value; return AC_OK; }
+  if (key == 3 && (value == 0 || value == 1)) { g_tc_l2hint = value; return AC_OK; }
   return AC_ERR_INVALID;
 }
 
@@ -654,9 +727,13 @@ extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn
   if (Mq == 0) return AC_OK;
   if (!ws || ws_bytes < 256) return AC_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  AC_CUDA(cudaMemsetAsync(ws, 0, 256, st));
   // column minima are accumulated with atomicMin on the fp32 bit pattern: start from a huge finite value
-  AC_CUDA(cudaMemsetAsync(colmin_d2, 0x7f, (size_t)(Mq / P) * nb_img * P * sizeof(float), st));
+  {
+    const long long words = (long long)(Mq / P) * nb_img * P;
+    const int blocks = (int)std::min<long long>((words + 1023) / 1024, 148LL * 8);
+    fill_u32_kernel<<<blocks, 256, 0, st>>>((unsigned int*)colmin_d2, words, 0x7f7f7f7fu);
+    AC_LAUNCH_CHECK();
+  }
   return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, rowmin_d2, (int*)ws, st, 1, q_img0,
                            (unsigned int*)colmin_d2, (char*)ws + 256, ws_bytes - 256);
 }
@@ -677,7 +754,7 @@ extern "C" size_t ac_min_dist_workspace_bytes(int64_t Mq, int nb_img, int P, int
   // 256 B pipeline-watchdog flag + (symmetric form) the raster list of (query block, bank image) units
   const long long mblocks = (Mq + 127) / 128;
   const long long per_mb = std::min<long long>(nb_img, nb_img / 2 + 64 * 256 / std::max(1, P) + 2);
-  return 256 + (size_t)(mblocks * per_mb) * sizeof(int2);
+  return 256 + 16 + (size_t)(mblocks * per_mb) * sizeof(int2);
 }
 
 extern "C" int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
@@ -693,6 +770,7 @@ extern "C" int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, i
     return launch_mindist_simt((const float*)Qhi, Mq, (const float*)Bhi, nb_img, P, D, dmin, st);
   if (!Qn2 || !Bn2) return AC_ERR_INVALID;
   if (!ws || ws_bytes < 256) return AC_ERR_WORKSPACE;
-  AC_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+  fill_u32_kernel<<<1, 64, 0, st>>>((unsigned int*)ws, 64, 0u);   // watchdog flag (no copy-engine memset)
+  AC_LAUNCH_CHECK();
   return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, dmin, (int*)ws, st);
 }
