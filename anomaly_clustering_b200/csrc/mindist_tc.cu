@@ -675,6 +675,20 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
     prm.n_units = d_n;
     prm.total_units = max_units;   // upper bound (sizes the grid); the kernel reads the exact count
   }
+  prm.idesc_main = make_idesc(kTileM * G, wmain, bf16);
+  prm.idesc_last = make_idesc(kTileM * G, wlast, bf16);
+  const long long brows = (long long)nb_img * P;
+  int rc;
+  if ((rc = make_map(&prm.mapA[0], Qhi, Mq, D, kTileM, bf16))) return rc;
+  if ((rc = make_map(&prm.mapBmain[0], Bhi, brows, D, wmain / G, bf16))) return rc;
+  if ((rc = make_map(&prm.mapBlast[0], Bhi, brows, D, wlast / G, bf16))) return rc;
+  if (x3) {
+    if ((rc = make_map(&prm.mapA[1], Qlo, Mq, D, kTileM, bf16))) return rc;
+    if ((rc = make_map(&prm.mapBmain[1], Blo, brows, D, wmain / G, bf16))) return rc;
+    if ((rc = make_map(&prm.mapBlast[1], Blo, brows, D, wlast / G, bf16))) return rc;
+  } else {
+    prm.mapA[1] = prm.mapA[0]; prm.mapBmain[1] = prm.mapBmain[0]; prm.mapBlast[1] = prm.mapBlast[0];
+  }
   int dev = 0, num_sms = 0;
   AC_CUDA(cudaGetDevice(&dev));
   AC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
