@@ -95,6 +95,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch
         fn.restype = res
         fn.argtypes = args
+    lib.ac_debug_launches.restype = ctypes.c_ulonglong
+    lib.ac_debug_launches.argtypes = []
     lib.ac_debug_set.restype = c_int
     lib.ac_debug_set.argtypes = [c_int, c_int]
     _lib = lib

@@ -13,6 +13,7 @@
 namespace ac {
 
 extern thread_local int g_last_cuda_error;
+extern unsigned long long g_kernel_launches;   // kernels launched by this library (bench.py reports it)
 
 inline int cuda_fail(cudaError_t e) {
   g_last_cuda_error = (int)e;
@@ -25,7 +26,11 @@ inline int cuda_fail(cudaError_t e) {
     if (_e != cudaSuccess) return ::ac::cuda_fail(_e);  \
   } while (0)
 
-#define AC_LAUNCH_CHECK() AC_CUDA(cudaGetLastError())
+#define AC_LAUNCH_CHECK()                                        \
+  do {                                                           \
+    __atomic_fetch_add(&::ac::g_kernel_launches, 1ull, __ATOMIC_RELAXED); \
+    AC_CUDA(cudaGetLastError());                                 \
+  } while (0)
 
 // 0 when the current device is CC 10.x.
 int check_device();

@@ -631,6 +631,7 @@ static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   AC_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
+  __atomic_fetch_add(&g_kernel_launches, 1ull, __ATOMIC_RELAXED);
   return AC_OK;
 }
 

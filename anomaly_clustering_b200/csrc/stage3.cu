@@ -13,6 +13,7 @@
 namespace ac {
 
 thread_local int g_last_cuda_error = 0;
+unsigned long long g_kernel_launches = 0;
 
 int check_device() {
   int dev = 0;
@@ -234,6 +235,9 @@ extern "C" const char* ac_strerror(int code) {
 }
 
 extern "C" int ac_last_cuda_error(void) { return g_last_cuda_error; }
+
+// test / bench hook (not in the public header): kernels launched by the library so far
+extern "C" unsigned long long ac_debug_launches(void) { return __atomic_load_n(&g_kernel_launches, __ATOMIC_RELAXED); }
 
 extern "C" int ac_device_ok(int dev) {
   int major = 0;

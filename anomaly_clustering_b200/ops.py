@@ -15,13 +15,9 @@ _OP_DTYPES = {"f16": (torch.float16, _lib.AC_DT_F16), "bf16": (torch.bfloat16, _
 _TORCH_TO_AC = {torch.float32: _lib.AC_DT_F32, torch.float16: _lib.AC_DT_F16, torch.bfloat16: _lib.AC_DT_BF16}
 
 
-# number of libac_b200 kernels launched through this module (bench.py reports it as gpu_launches)
-LAUNCHES = 0
-
-
-def _count(n: int) -> None:
-    global LAUNCHES
-    LAUNCHES += n
+def launches() -> int:
+    """Kernels launched by libac_b200 so far, counted inside the library (bench.py: gpu_launches)."""
+    return int(_lib.load().ac_debug_launches())
 
 
 def _stream() -> int:
@@ -110,7 +106,6 @@ def embed(
     rc = lib.ac_embed(arr, L, B, patchsize, stride, pretrain_dim, target_dim, int(layernorm), float(eps), _ptr(Z), _ptr(hi),
                       _ptr(lo), op_code, _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_embed")
-    _count((1 if layernorm else 0) + L)  # LayerNorm statistics pass + one fused embed launch per layer
     return Z, hi, lo, (h, w)
 
 
@@ -123,7 +118,6 @@ def patchify(x: torch.Tensor, patchsize: int, stride: int):
     out = torch.empty(B, h * w, C, patchsize, patchsize, dtype=torch.float32, device=x.device)
     grid = (ctypes.c_int * 2)()
     check(lib.ac_patchify(_ptr(x), B, C, H, W, patchsize, stride, _ptr(out), grid, _stream()), "ac_patchify")
-    _count(1)
     return out, [int(grid[0]), int(grid[1])]
 
 
@@ -133,7 +127,6 @@ def adaptive_pool1d(x: torch.Tensor, out_dim: int) -> torch.Tensor:
     x2 = x.reshape(len(x), -1).contiguous().float()
     out = torch.empty(x2.shape[0], out_dim, dtype=torch.float32, device=x.device)
     check(lib.ac_adaptive_pool1d(_ptr(x2), x2.shape[0], x2.shape[1], out_dim, _ptr(out), _stream()), "ac_adaptive_pool1d")
-    _count(1)
     return out
 
 
@@ -145,7 +138,6 @@ def split_operand(x: torch.Tensor, operand: str, want_lo: bool):
     hi = torch.empty(x.shape, dtype=tdt, device=x.device)
     lo = torch.empty(x.shape, dtype=tdt, device=x.device) if want_lo else None
     check(lib.ac_split_operand(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), code, _stream()), "ac_split_operand")
-    _count(1)
     return hi, lo
 
 
@@ -155,7 +147,6 @@ def row_norms(A: torch.Tensor, A2: Optional[torch.Tensor] = None) -> torch.Tenso
     assert A.dim() == 2 and A.is_contiguous()
     out = torch.empty(A.shape[0], dtype=torch.float32, device=A.device)
     check(lib.ac_row_norms(_ptr(A), _ptr(A2), _TORCH_TO_AC[A.dtype], A.shape[0], A.shape[1], _ptr(out), _stream()), "ac_row_norms")
-    _count(1)
     return out
 
 
@@ -173,7 +164,6 @@ def min_dist(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, 
     rc = lib.ac_min_dist(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec, _ptr(dmin),
                          _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_min_dist")
-    _count(1)
     return dmin
 
 
@@ -191,7 +181,6 @@ def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int,
     rc = lib.ac_min_dist_sym(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
                              _ptr(rowmin), _ptr(colmin), _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_min_dist_sym")
-    _count(1)
     return rowmin, colmin
 
 
@@ -202,7 +191,6 @@ def reduce_weights_sym(rowmin: torch.Tensor, colfull: torch.Tensor, Pq: int, q_i
     assert colfull.shape == rowmin.shape and colfull.is_contiguous() and rowmin.is_contiguous()
     w = torch.empty(Mq, dtype=torch.float32, device=rowmin.device)
     check(lib.ac_reduce_weights_sym(_ptr(rowmin), _ptr(colfull), Mq, nb_img, Pq, q_img0, _ptr(w), _stream()), "ac_reduce_weights_sym")
-    _count(1)
     return w
 
 
@@ -215,7 +203,6 @@ def reduce_weights(dmin: torch.Tensor, Pq: int, q_self: Optional[torch.Tensor], 
     if q_self is not None:
         assert q_self.dtype == torch.int32 and q_self.numel() * Pq >= Mq
     check(lib.ac_reduce_weights(_ptr(dmin), Mq, nb_img, Pq, _ptr(q_self), m, _ptr(w), _stream()), "ac_reduce_weights")
-    _count(1)
     return w
 
 
@@ -230,7 +217,6 @@ def alpha(w: torch.Tensor, taus: Sequence[float], want64: bool = True, want32: b
     a32 = torch.empty(T, N, P, dtype=torch.float32, device=w.device) if want32 else None
     tarr = (ctypes.c_double * T)(*[float(t) for t in taus])
     check(lib.ac_alpha(_ptr(w), N, P, tarr, T, _ptr(a64), _ptr(a32), _stream()), "ac_alpha")
-    _count(1)
     return a64, a32
 
 
@@ -242,7 +228,6 @@ def weighted_embed(alpha32: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
     assert Z.is_contiguous() and Z.dtype == torch.float32
     X = torch.empty(N, D, dtype=torch.float32, device=Z.device)
     check(lib.ac_weighted_embed(_ptr(a), _ptr(Z), N, P, D, _ptr(X), _stream()), "ac_weighted_embed")
-    _count(1)
     return X
 
 
@@ -253,5 +238,4 @@ def pairwise_l2(X: torch.Tensor) -> torch.Tensor:
     N, D = X.shape
     out = torch.empty(N, N, dtype=torch.float32, device=X.device)
     check(lib.ac_pairwise_l2(_ptr(X), N, D, _ptr(out), _stream()), "ac_pairwise_l2")
-    _count(1)
     return out

@@ -231,7 +231,7 @@ def main():
         step(feats)
     sync_all()
     pipeline.PROFILE = []
-    launches0 = ops.LAUNCHES
+    launches0 = ops.launches()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -247,7 +247,7 @@ def main():
     if args.cuda_profiler:
         torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
-    launches = ops.LAUNCHES - launches0
+    launches = ops.launches() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
     marks = pipeline.PROFILE
     pipeline.PROFILE = None
