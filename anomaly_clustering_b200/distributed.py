@@ -52,19 +52,30 @@ def lpt_assign(costs: Sequence[float], world: int) -> List[List[int]]:
 
 def all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
     """All-gather row blocks of unequal length: local [counts[rank], ...] -> [sum(counts), ...].
-    Equal-size padded all_gather_into_tensor (one NCCL call) + compaction when counts differ."""
+
+    NCCL: every rank's block lands directly in its slice of the result (equal counts: one
+    all_gather_into_tensor; unequal: torch's grouped-broadcast all_gather on views) -- no padding and no
+    compaction copy of the gathered bank.  gloo (CPU tests): padded all_gather_into_tensor + compaction."""
     world = dist.get_world_size(group)
-    mx = max(counts)
     tail = tuple(local.shape[1:])
-    if local.shape[0] == mx:
-        send = local.contiguous()
-    else:
-        send = torch.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
-        send[: local.shape[0]] = local
+    local = local.contiguous()
+    if all(c == counts[0] for c in counts):
+        buf = torch.empty((sum(counts),) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(buf, local, group=group)
+        return buf
+    if dist.get_backend(group) == "nccl":
+        buf = torch.empty((sum(counts),) + tail, dtype=local.dtype, device=local.device)
+        views, start = [], 0
+        for c in counts:
+            views.append(buf[start:start + c])
+            start += c
+        dist.all_gather(views, local, group=group)
+        return buf
+    mx = max(counts)
+    send = torch.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
+    send[: local.shape[0]] = local
     buf = torch.empty((world * mx,) + tail, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(buf, send, group=group)
-    if all(c == mx for c in counts):
-        return buf
     return torch.cat([buf[r * mx : r * mx + counts[r]] for r in range(world)], dim=0)
 
 

@@ -38,6 +38,9 @@ WORKLOADS = {
     "config4": dict(
         name="config4 (joint bank): 1210 synthetic images x 784 patches (10 MVTec-object-sized categories), 2048->4096, unsupervised tau=1",
         layers=[(768, 28, 28, True), (768, 28, 28, True)], n_img=1210, Dp=2048, D=4096, tau=1.0),
+    "tiny13": dict(
+        name="tiny13: 2x[96,12,12] tokens, 13 images x 144 patches, 256->512 (uneven shards on 2+ ranks; CI smoke)",
+        layers=[(96, 12, 12, True), (96, 12, 12, True)], n_img=13, Dp=256, D=512, tau=1.0),
     "tiny": dict(
         name="tiny: 2x[96,12,12] tokens, 12 images x 144 patches, 256->512 (CI smoke of the bench itself)",
         layers=[(96, 12, 12, True), (96, 12, 12, True)], n_img=12, Dp=256, D=512, tau=1.0),
