@@ -144,6 +144,7 @@ def run_path_sharded(
     assert q.n_img == hi_i - lo_i
     P = q.P
     row_counts = [(b - a) * P for a, b in bounds]
+    pipeline._mark("gather_begin")
     if precision == "f32":
         bank = pipeline.PatchSet(n_total, P, q.D, q.grid, Z=all_gather_rows(q.Z, row_counts, group))
     else:
@@ -153,13 +154,16 @@ def run_path_sharded(
             lo=None if q.lo is None else all_gather_rows(q.lo, row_counts, group),
             n2=all_gather_rows(q.n2, row_counts, group),
         )
+    pipeline._mark("gather_end")
     if symmetric and precision != "f32" and P >= 32 and hasattr(compute, "min_dist_sym"):
         # every unordered image pair is multiplied once, by the rank that owns the pair's first image;
         # the column minima it produces for other ranks' query rows travel in one small all-to-all
         pipeline._mark("mindist_begin")
         rowmin, colmin = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision)
         pipeline._mark("mindist_end")
+        pipeline._mark("exchange_begin")
         colfull = exchange_colmin(colmin, bounds, P, group)
+        pipeline._mark("exchange_end")
         w = compute.reduce_weights_sym(rowmin, colfull, P, lo_i).reshape(q.n_img, P)
     else:
         q_self = torch.arange(lo_i, hi_i, dtype=torch.int32, device=q.Z.device)
@@ -167,6 +171,8 @@ def run_path_sharded(
     a64, a32 = compute.alpha(w, list(taus))
     Z3 = q.Z.reshape(q.n_img, P, q.D)
     X_loc = torch.stack([compute.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)  # [n_r, T, D]
+    pipeline._mark("xgather_begin")
     X_all = all_gather_rows(X_loc, [b - a for a, b in bounds], group).permute(1, 0, 2).contiguous()  # [T, N, D]
+    pipeline._mark("xgather_end")
     Dm = torch.stack([compute.pairwise_l2(X_all[t]) for t in range(len(taus))])
     return a64, X_all, Dm, w

@@ -265,6 +265,7 @@ def main():
         e_ = [e for n, e in marks if n == tag + "_end"]
         return [x.elapsed_time(y) for x, y in zip(b, e_)]
 
+    comm = {t: sum(span(t)) / max(1, args.steps) for t in ("gather", "exchange", "xgather")} if world > 1 else {}
     md = span("mindist")
     md_ms = sum(md) / max(1, len(md))
     emb = span("embed")
@@ -394,7 +395,8 @@ def main():
                          else "algorithmic = executed (all-pairs kernel)",
                          "algorithmic_flops_per_launch": flops, "algorithmic_tflops": alg_tflops, "traffic": traffic},
             "stages": {"embed_ms_per_step": emb_ms, "embed_GBps": embed_gbs, "embed_frac_of_hbm": embed_gbs / peaks["hbm_gbs"],
-                       "mindist_ms_per_step": md_ms, "other_ms_per_step": elapsed_ms / args.steps - emb_ms - md_ms},
+                       "mindist_ms_per_step": md_ms, "other_ms_per_step": elapsed_ms / args.steps - emb_ms - md_ms,
+                       "comm_ms_per_step_rank0": comm},
             "cpu_baseline": cpu_baseline,
         }
         sys.stdout.flush()
