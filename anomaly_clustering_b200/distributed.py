@@ -110,7 +110,7 @@ def run_path_sharded(
     pretrain_dim: int,
     target_dim: int,
     taus: Sequence[float] = (1.0,),
-    precision: str = "f16",
+    precision: str = "auto",
     group=None,
     compute=None,
     symmetric: bool = True,
@@ -123,6 +123,7 @@ def run_path_sharded(
     can be exercised on CPU with gloo; the default is the CUDA library and nothing else."""
     from . import pipeline
 
+    precision = pipeline.resolve_precision(precision, taus)
     if compute is None:
         from . import ops
 

@@ -42,7 +42,7 @@ def make_category_data(
     train_dataloader: Optional[Iterable] = None,
     backbone: Optional[torch.nn.Module] = None,
     device: Optional[torch.device] = None,
-    precision: str = "f16",
+    precision: str = "auto",
     batch_size: int = 16,
     input_shape=(3, 224, 224),
 ):
@@ -60,6 +60,9 @@ def make_category_data(
         pretrain_embed_dimension=pretrain_embed_dimension, target_embed_dimension=target_embed_dimension, patchsize=patchsize,
     )
 
+    taus_early = [float(t) for t in (tau if isinstance(tau, (list, tuple)) else [tau])]
+    precision = pipeline.resolve_precision(precision, taus_early)
+
     def embed_all(loader, want_z):
         """Backbone (torch) + fused embed, `batch_size` images at a time; everything stays on the device."""
         ims = _images(loader)
@@ -73,7 +76,7 @@ def make_category_data(
         return pipeline.PatchSet(sum(s.n_img for s in sets), first.P, first.D, first.grid, cat([s.Z for s in sets]),
                                  cat([s.hi for s in sets]), cat([s.lo for s in sets]), cat([s.n2 for s in sets]))
 
-    taus: List[float] = [float(t) for t in (tau if isinstance(tau, (list, tuple)) else [tau])]
+    taus: List[float] = taus_early
     q = embed_all(test_dataloader, want_z=True)
     if supervised == "supervised":
         if train_dataloader is None:

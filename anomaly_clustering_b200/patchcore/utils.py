@@ -12,7 +12,7 @@ import torch
 
 from .. import ops, pipeline
 
-PRECISION = "f16"   # f16 | bf16 | f16x3 | bf16x3 | f32 (precision table)
+PRECISION = "auto"  # auto | f16 | bf16 | f16x3 | bf16x3 | f32; auto = f16, or f16x3 for 0 < tau < 0.5
 
 _cache: Dict[Tuple, pipeline.PatchSet] = {}
 
@@ -39,9 +39,13 @@ def _rows(ps: pipeline.PatchSet, i: int) -> pipeline.PatchSet:
     return pipeline.PatchSet(1, ps.P, ps.D, ps.grid, pick(ps.Z), pick(ps.hi), pick(ps.lo), pick(ps.n2))
 
 
+def _prec(precision, taus):
+    return pipeline.resolve_precision(precision or PRECISION, taus)
+
+
 def Weight_Distance_Unsupervised(Z, i, device, precision: Optional[str] = None):
     """utils.py:222-227 -> w_i [P]: mean over j != i of min_q ||Z[i,p] - Z[j,q]||."""
-    precision = precision or PRECISION
+    precision = _prec(precision, [0.1])     # tau unknown here: assume the most demanding one
     ps = _patchset(_to_device(Z, device), precision)
     q_self = torch.tensor([i], dtype=torch.int32, device=ps.Z.device)
     return pipeline.min_distance_weights(_rows(ps, i), ps, "unsupervised", precision, q_self=q_self)[0]
@@ -49,7 +53,7 @@ def Weight_Distance_Unsupervised(Z, i, device, precision: Optional[str] = None):
 
 def Weight_Distance_Supervised(Z, Z_train, i, device, precision: Optional[str] = None):
     """utils.py:230-237 -> w_i [P]: min over bank images and bank patches."""
-    precision = precision or PRECISION
+    precision = _prec(precision, [0.1])
     ps = _patchset(_to_device(Z, device), precision)
     bank = pipeline.patchset_from_Z(_to_device(Z_train, device), precision)
     return pipeline.min_distance_weights(_rows(ps, i), bank, "supervised", precision)[0]
@@ -63,7 +67,7 @@ def _alpha(w: torch.Tensor, tau: float) -> torch.Tensor:
 def Matrix_Alpha_Unsupervised(tau, k, Z, device, precision: Optional[str] = None):
     """utils.py:240-257 -> [N,P] float64 (k cancels in the normalisation, as in the reference)."""
     print("{:-^80}".format("Calculating Unsupervised Alpha Matrix"))
-    precision = precision or PRECISION
+    precision = _prec(precision, [tau])
     ps = _patchset(_to_device(Z, device), precision)
     return _alpha(pipeline.min_distance_weights(ps, ps, "unsupervised", precision), tau)
 
@@ -71,7 +75,7 @@ def Matrix_Alpha_Unsupervised(tau, k, Z, device, precision: Optional[str] = None
 def Matrix_Alpha_Supervised(tau, k, Z, Z_train, device, precision: Optional[str] = None):
     """utils.py:260-277 -> [N,P] float64."""
     print("{:-^80}".format("Calculating Supervised Alpha Matrix"))
-    precision = precision or PRECISION
+    precision = _prec(precision, [tau])
     ps = _patchset(_to_device(Z, device), precision)
     bank = pipeline.patchset_from_Z(_to_device(Z_train, device), precision)
     return _alpha(pipeline.min_distance_weights(ps, bank, "supervised", precision), tau)

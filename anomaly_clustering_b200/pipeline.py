@@ -35,6 +35,16 @@ def _mark(tag: str) -> None:
         PROFILE.append((tag, ev))
 
 
+def resolve_precision(precision: str, taus: Sequence[float]) -> str:
+    """'auto' -> the cheapest mode that keeps alpha inside the 1e-3 max-abs tolerance, from the measured table
+    in DESIGN.md section 5 (config-2 scale): one fp16 pass for tau >= 0.5 (and for tau = 0, the arg-max),
+    split-fp16 (3 passes) for 0 < tau < 0.5."""
+    if precision != "auto":
+        return precision
+    small = [t for t in taus if 0.0 < abs(float(t)) < 0.5]
+    return "f16x3" if small else "f16"
+
+
 _OPERAND_OF = {"f16": ("f16", False), "bf16": ("bf16", False), "f16x3": ("f16", True), "bf16x3": ("bf16", True), "f32": (None, False)}
 
 
@@ -179,10 +189,11 @@ def run_path(
     mode: str = "unsupervised",
     taus: Sequence[float] = (1.0,),
     bank_features: Optional[Sequence[torch.Tensor]] = None,
-    precision: str = "f16",
+    precision: str = "auto",
     layernorm: bool = True,
 ) -> PathResult:
     """Single-GPU hot path: hooked features (device tensors) -> PathResult (device tensors)."""
+    precision = resolve_precision(precision, taus)
     q = embed_images(features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=True, layernorm=layernorm)
     w = None
     if mode == "unsupervised":
