@@ -8,6 +8,7 @@ w_i, alpha_i and X_i depend only on query image i and the read-only bank
 On CPU (gloo) the same sharding / gather logic is exercised by tests with a stand-in compute."""
 from __future__ import annotations
 
+import functools
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -79,6 +80,57 @@ def all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None) -> t
     return torch.cat([buf[r * mx : r * mx + counts[r]] for r in range(world)], dim=0)
 
 
+def needed_shards(bounds: Sequence[Tuple[int, int]], n_total: int) -> List[List[int]]:
+    return [list(x) for x in _needed_shards(tuple(tuple(b) for b in bounds), n_total)]
+
+
+@functools.lru_cache(maxsize=64)
+def _needed_shards(bounds: Tuple[Tuple[int, int], ...], n_total: int):
+    """Symmetric form: need[r] = ranks whose images appear as BANK images of pairs owned by rank r's
+    query images (the circular window of the next n_total//2 images) -- about half of the other ranks."""
+    world = len(bounds)
+    owner = [0] * n_total
+    for s, (a, b) in enumerate(bounds):
+        for i in range(a, b):
+            owner[i] = s
+    need = []
+    for r, (a, b) in enumerate(bounds):
+        ranks = set()
+        for i in range(a, b):
+            for d in range(1, n_total // 2 + 1):
+                j = (i + d) % n_total
+                if pair_owned(i, j, n_total):
+                    ranks.add(owner[j])
+        ranks.discard(r)
+        need.append(tuple(sorted(ranks)))
+    return tuple(need)
+
+
+def gather_needed_rows(local: torch.Tensor, bounds: Sequence[Tuple[int, int]], rows_per_item: int, need: Sequence[Sequence[int]],
+                       group=None) -> torch.Tensor:
+    """Like all_gather_rows, but a rank only receives the shards listed in need[rank]; the rest of the
+    returned [sum rows, ...] buffer stays uninitialised (the symmetric kernel never touches it).
+    Point-to-point NCCL sends/receives in one batch: roughly half the all-gather volume."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    total = bounds[-1][1] * rows_per_item
+    buf = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    a, b = bounds[rank]
+    buf[a * rows_per_item : b * rows_per_item].copy_(local)
+    local = local.contiguous()
+    ops_ = []
+    for dst in range(world):
+        if dst != rank and rank in need[dst] and local.shape[0] > 0:
+            ops_.append(dist.P2POp(dist.isend, local, dst, group=group))
+    for src in need[rank]:
+        sa, sb = bounds[src]
+        if sb > sa:
+            ops_.append(dist.P2POp(dist.irecv, buf[sa * rows_per_item : sb * rows_per_item], src, group=group))
+    if ops_:
+        for req in dist.batch_isend_irecv(ops_):
+            req.wait()
+    return buf
+
+
 def exchange_colmin(colmin: torch.Tensor, bounds: Sequence[Tuple[int, int]], P: int, group=None) -> torch.Tensor:
     """Symmetric mode: rank r holds colmin [n_r, N*P] = (its images as BANK image, every global query
     row); the owner of query rows [a*P, b*P) needs those columns from every rank.  All-to-all of the
@@ -145,8 +197,19 @@ def run_path_sharded(
     assert q.n_img == hi_i - lo_i
     P = q.P
     row_counts = [(b - a) * P for a, b in bounds]
+    use_sym = symmetric and precision != "f32" and P >= 32 and hasattr(compute, "min_dist_sym")
     pipeline._mark("gather_begin")
-    if precision == "f32":
+    if use_sym:
+        # only the shards that hold bank images of pairs this rank owns (the next n_total//2 images)
+        need = needed_shards(bounds, n_total)
+        img_rows = P
+        bank = pipeline.PatchSet(
+            n_total, P, q.D, q.grid,
+            hi=gather_needed_rows(q.hi, bounds, img_rows, need, group),
+            lo=None if q.lo is None else gather_needed_rows(q.lo, bounds, img_rows, need, group),
+            n2=gather_needed_rows(q.n2, bounds, img_rows, need, group),
+        )
+    elif precision == "f32":
         bank = pipeline.PatchSet(n_total, P, q.D, q.grid, Z=all_gather_rows(q.Z, row_counts, group))
     else:
         bank = pipeline.PatchSet(
@@ -156,7 +219,7 @@ def run_path_sharded(
             n2=all_gather_rows(q.n2, row_counts, group),
         )
     pipeline._mark("gather_end")
-    if symmetric and precision != "f32" and P >= 32 and hasattr(compute, "min_dist_sym"):
+    if use_sym:
         # every unordered image pair is multiplied once, by the rank that owns the pair's first image;
         # the column minima it produces for other ranks' query rows travel in one small all-to-all
         pipeline._mark("mindist_begin")

@@ -27,6 +27,20 @@ def test_pair_ownership_covers_every_pair_once():
             assert max(per_image) - min(per_image) <= 1     # balanced: each image owns ~(n-1)/2 pairs
 
 
+def test_needed_shards_cover_owned_pairs_only():
+    for n, world in ((100, 8), (13, 2), (21, 4), (5, 3), (1210, 8)):
+        bounds = distributed.shard_bounds(n, world)
+        need = distributed.needed_shards(bounds, n)
+        owner = [r for r, (a, b) in enumerate(bounds) for _ in range(a, b)]
+        step = max(1, n // 60)
+        for r, (a, b) in enumerate(bounds):
+            want = {owner[j] for i in range(a, b, step) for j in range(n) if distributed.pair_owned(i, j, n)} - {r}
+            assert want <= set(need[r])
+            assert r not in need[r]
+        if world == 8 and n == 100:
+            assert max(len(x) for x in need) <= 5      # about half of the 7 other ranks
+
+
 def test_shard_bounds_and_lpt():
     assert distributed.shard_bounds(100, 8) == [(0, 13), (13, 26), (26, 39), (39, 52), (52, 64), (64, 76), (76, 88), (88, 100)]
     assert distributed.shard_bounds(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
