@@ -66,8 +66,8 @@ SIGNATURES = {
     ),
     "ac_min_dist_sym": (
         c_int,
-        [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-         c_void_p, c_void_p, c_size_t, c_void_p],
+        [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+         c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
     "ac_reduce_weights_sym": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ac_reduce_weights": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),

@@ -58,6 +58,7 @@ struct __align__(64) TcParams {
   unsigned int* colmin;      // [nq_img, nb_img*P] squared distances (fp32 bits), atomicMin target
   const int2* units;         // sym mode: explicit (query block, bank image) list in raster order (device-built)
   const long long* n_units;  // sym mode: length of that list (device memory)
+  int win_begin, win_count;  // sym mode: only bank images in the circular window [win_begin, win_begin + win_count)
 };
 
 // Ownership of the unordered pair {i, j} of N images: the image that sees the other one within the
@@ -507,6 +508,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
 // per launch while the next category's features were being uploaded.)  Single CTA: row r = (group, k)
 // of the raster, count its active query blocks, block-wide exclusive scan, then emit.
 __device__ __forceinline__ bool unit_has_work(const TcParams& p, int G, int mb, int img) {
+  int dw = img - p.win_begin;
+  if (dw < 0) dw += p.nb_img;
+  if (dw >= p.win_count) return false;          // bank image outside this launch's window
   const long long rows_per_mb = (long long)kTileM * G;
   const long long r0 = (long long)mb * rows_per_mb, r1 = min(p.Mq, r0 + rows_per_mb) - 1;
   const int i0 = p.q_img0 + (int)(r0 / p.P), i1 = p.q_img0 + (int)(r1 / p.P);
@@ -637,7 +641,8 @@ static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {
 
 int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long long Mq, const void* Bhi, const void* Blo,
                       const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int* err_flag, cudaStream_t st,
-                      int sym = 0, int q_img0 = 0, unsigned int* colmin = nullptr, void* unit_ws = nullptr, size_t unit_ws_bytes = 0) {
+                      int sym = 0, int q_img0 = 0, unsigned int* colmin = nullptr, void* unit_ws = nullptr, size_t unit_ws_bytes = 0,
+                      int win_begin = 0, int win_count = -1) {
   const bool bf16 = (precision == AC_PREC_BF16 || precision == AC_PREC_BF16X3);
   const bool x3 = (precision == AC_PREC_F16X3 || precision == AC_PREC_BF16X3);
   if (D % 8 != 0) return AC_ERR_UNSUPPORTED;  // TMA needs a 16-byte row pitch
@@ -659,6 +664,7 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.GM = g_tc_gm;
   prm.l2_hint = g_tc_l2hint;
   prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin; prm.units = nullptr;
+  prm.win_begin = win_begin; prm.win_count = (win_count < 0) ? nb_img : win_count;
   // bank images a raster group of GM query blocks can own: N/2 after each of the images it spans
   prm.KU = std::min(nb_img, nb_img / 2 + (int)(((long long)prm.GM * kTileM * G - 1) / P) + 1);
   prm.total_units = (long long)prm.n_mblocks * nb_img;
@@ -730,10 +736,12 @@ __global__ void reduce_weights_sym_kernel(const float* __restrict__ rowmin, cons
 }
 
 extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
-                               const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, float* rowmin_d2,
-                               float* colmin_d2, void* ws, size_t ws_bytes, ac_stream_t stream) {
+                               const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                               int bank_count, int init_colmin, float* rowmin_d2, float* colmin_d2, void* ws, size_t ws_bytes,
+                               ac_stream_t stream) {
   if (!Qhi || !Bhi || !Qn2 || !Bn2 || !rowmin_d2 || !colmin_d2 || Mq < 0 || nb_img < 1 || P < 1 || D < 1 || q_img0 < 0)
     return AC_ERR_INVALID;
+  if (bank_begin < 0 || bank_begin >= nb_img || bank_count < 0 || bank_count > nb_img) return AC_ERR_INVALID;
   if (precision < AC_PREC_F16 || precision > AC_PREC_BF16X3) return AC_ERR_UNSUPPORTED;  // tensor-core modes only
   if (P < 32 || Mq % P != 0) return AC_ERR_UNSUPPORTED;  // a warp of 32 rows may span at most two query images
   if (q_img0 + Mq / P > nb_img) return AC_ERR_INVALID;
@@ -743,14 +751,14 @@ extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn
   if (!ws || ws_bytes < 256) return AC_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   // column minima are accumulated with atomicMin on the fp32 bit pattern: start from a huge finite value
-  {
+  if (init_colmin) {
     const long long words = (long long)(Mq / P) * nb_img * P;
     const int blocks = (int)std::min<long long>((words + 1023) / 1024, 148LL * 8);
     fill_u32_kernel<<<blocks, 256, 0, st>>>((unsigned int*)colmin_d2, words, 0x7f7f7f7fu);
     AC_LAUNCH_CHECK();
   }
   return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, rowmin_d2, (int*)ws, st, 1, q_img0,
-                           (unsigned int*)colmin_d2, (char*)ws + 256, ws_bytes - 256);
+                           (unsigned int*)colmin_d2, (char*)ws + 256, ws_bytes - 256, bank_begin, bank_count);
 }
 
 extern "C" int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,

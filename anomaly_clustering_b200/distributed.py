@@ -106,17 +106,18 @@ def _needed_shards(bounds: Tuple[Tuple[int, int], ...], n_total: int):
     return tuple(need)
 
 
-def gather_needed_rows(local: torch.Tensor, bounds: Sequence[Tuple[int, int]], rows_per_item: int, need: Sequence[Sequence[int]],
-                       group=None) -> torch.Tensor:
+def start_gather_needed_rows(local: torch.Tensor, bounds: Sequence[Tuple[int, int]], rows_per_item: int,
+                             need: Sequence[Sequence[int]], group=None):
     """Like all_gather_rows, but a rank only receives the shards listed in need[rank]; the rest of the
     returned [sum rows, ...] buffer stays uninitialised (the symmetric kernel never touches it).
-    Point-to-point NCCL sends/receives in one batch: roughly half the all-gather volume."""
+    Point-to-point NCCL sends/receives in one batch (roughly half the all-gather volume), left IN FLIGHT:
+    returns (buffer, requests); the caller waits on the requests before touching remote shards."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     total = bounds[-1][1] * rows_per_item
     buf = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     a, b = bounds[rank]
-    buf[a * rows_per_item : b * rows_per_item].copy_(local)
     local = local.contiguous()
+    buf[a * rows_per_item : b * rows_per_item].copy_(local)
     ops_ = []
     for dst in range(world):
         if dst != rank and rank in need[dst] and local.shape[0] > 0:
@@ -125,9 +126,14 @@ def gather_needed_rows(local: torch.Tensor, bounds: Sequence[Tuple[int, int]], r
         sa, sb = bounds[src]
         if sb > sa:
             ops_.append(dist.P2POp(dist.irecv, buf[sa * rows_per_item : sb * rows_per_item], src, group=group))
-    if ops_:
-        for req in dist.batch_isend_irecv(ops_):
-            req.wait()
+    reqs = dist.batch_isend_irecv(ops_) if ops_ else []
+    return buf, reqs
+
+
+def gather_needed_rows(local, bounds, rows_per_item, need, group=None) -> torch.Tensor:
+    buf, reqs = start_gather_needed_rows(local, bounds, rows_per_item, need, group)
+    for r in reqs:
+        r.wait()
     return buf
 
 
@@ -186,6 +192,7 @@ def run_path_sharded(
             weighted_embed = staticmethod(ops.weighted_embed)
             pairwise_l2 = staticmethod(ops.pairwise_l2)
             min_dist_sym = staticmethod(ops.min_dist_sym)
+            supports_bank_window = True
             reduce_weights_sym = staticmethod(ops.reduce_weights_sym)
 
         compute = _Cuda
@@ -199,16 +206,16 @@ def run_path_sharded(
     row_counts = [(b - a) * P for a, b in bounds]
     use_sym = symmetric and precision != "f32" and P >= 32 and hasattr(compute, "min_dist_sym")
     pipeline._mark("gather_begin")
+    pending = []
     if use_sym:
-        # only the shards that hold bank images of pairs this rank owns (the next n_total//2 images)
+        # only the shards that hold bank images of pairs this rank owns (the next n_total//2 images);
+        # the transfers stay in flight while the pairs inside the local shard are multiplied
         need = needed_shards(bounds, n_total)
-        img_rows = P
-        bank = pipeline.PatchSet(
-            n_total, P, q.D, q.grid,
-            hi=gather_needed_rows(q.hi, bounds, img_rows, need, group),
-            lo=None if q.lo is None else gather_needed_rows(q.lo, bounds, img_rows, need, group),
-            n2=gather_needed_rows(q.n2, bounds, img_rows, need, group),
-        )
+        hi_buf, r1 = start_gather_needed_rows(q.hi, bounds, P, need, group)
+        lo_buf, r2 = (None, []) if q.lo is None else start_gather_needed_rows(q.lo, bounds, P, need, group)
+        n2_buf, r3 = start_gather_needed_rows(q.n2, bounds, P, need, group)
+        pending = list(r1) + list(r2) + list(r3)
+        bank = pipeline.PatchSet(n_total, P, q.D, q.grid, hi=hi_buf, lo=lo_buf, n2=n2_buf)
     elif precision == "f32":
         bank = pipeline.PatchSet(n_total, P, q.D, q.grid, Z=all_gather_rows(q.Z, row_counts, group))
     else:
@@ -222,9 +229,25 @@ def run_path_sharded(
     if use_sym:
         # every unordered image pair is multiplied once, by the rank that owns the pair's first image;
         # the column minima it produces for other ranks' query rows travel in one small all-to-all
-        pipeline._mark("mindist_begin")
-        rowmin, colmin = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision)
-        pipeline._mark("mindist_end")
+        two_phase = bool(pending) and q.n_img > 1 and getattr(compute, "supports_bank_window", False)
+        if two_phase:
+            # phase 1: bank images of the local shard (no remote data needed) overlaps the NCCL transfers
+            pipeline._mark("mindist_begin")
+            out = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,
+                                       bank_window=(lo_i, q.n_img), init=True)
+            pipeline._mark("mindist_end")
+            for r in pending:
+                r.wait()
+            pipeline._mark("mindist_begin")
+            rowmin, colmin = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,
+                                                  bank_window=(hi_i % n_total, n_total - q.n_img), init=False, out=out)
+            pipeline._mark("mindist_end")
+        else:
+            for r in pending:
+                r.wait()
+            pipeline._mark("mindist_begin")
+            rowmin, colmin = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision)
+            pipeline._mark("mindist_end")
         pipeline._mark("exchange_begin")
         colfull = exchange_colmin(colmin, bounds, P, group)
         pipeline._mark("exchange_end")

@@ -167,19 +167,26 @@ def min_dist(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, 
     return dmin
 
 
-def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str):
-    """Symmetric self-bank form: (rowmin_d2 [nb_img, Mq], colmin_d2 [Mq/P, nb_img*P]) squared distances."""
+def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str,
+                 bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None):
+    """Symmetric self-bank form: (rowmin_d2 [nb_img, Mq], colmin_d2 [Mq/P, nb_img*P]) squared distances.
+    bank_window=(begin, count) restricts the launch to a circular range of bank images; pass the previous
+    call's result as `out` with init=False to accumulate a second window into the same buffers."""
     lib = _lib.load()
     _need_cuda(Qhi, Bhi)
     prec = _lib.PRECISIONS[precision]
     Mq, D = Qhi.shape
     assert Bhi.shape == (nb_img * P, D) and Qhi.is_contiguous() and Bhi.is_contiguous()
-    rowmin = torch.empty(nb_img, Mq, dtype=torch.float32, device=Qhi.device)
-    colmin = torch.empty(Mq // P, nb_img * P, dtype=torch.float32, device=Qhi.device)
+    if out is None:
+        rowmin = torch.empty(nb_img, Mq, dtype=torch.float32, device=Qhi.device)
+        colmin = torch.empty(Mq // P, nb_img * P, dtype=torch.float32, device=Qhi.device)
+    else:
+        rowmin, colmin = out
+    begin, count = bank_window if bank_window is not None else (0, nb_img)
     ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
     rc = lib.ac_min_dist_sym(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
-                             _ptr(rowmin), _ptr(colmin), _ptr(ws), ws_bytes, _stream())
+                             int(begin), int(count), int(bool(init)), _ptr(rowmin), _ptr(colmin), _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_min_dist_sym")
     return rowmin, colmin
 

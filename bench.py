@@ -267,7 +267,7 @@ def main():
 
     comm = {t: sum(span(t)) / max(1, args.steps) for t in ("gather", "exchange", "xgather")} if world > 1 else {}
     md = span("mindist")
-    md_ms = sum(md) / max(1, len(md))
+    md_ms = sum(md) / max(1, args.steps)      # per step (the sharded path may split it into two launches)
     emb = span("embed")
     emb_ms = sum(emb) / max(1, args.steps)
     nq_local = hi_i - lo_i
@@ -389,7 +389,7 @@ def main():
                          "achieved": tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": tflops / peaks["bf16_sustained"], "peak_burst": peaks["bf16_burst"],
                          "frac_of_burst": tflops / peaks["bf16_burst"], "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
-                         "ms_per_launch": md_ms, "flops_per_launch": exec_flops,
+                         "ms_per_step": md_ms, "flops_per_launch": exec_flops,
                          "flops_counted": ("executed: each unordered image pair multiplied once (symmetric kernel); "
                                            "the all-pairs algorithmic count is algorithmic_flops_per_launch") if symmetric
                          else "algorithmic = executed (all-pairs kernel)",

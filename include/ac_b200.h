@@ -141,10 +141,14 @@ int ac_reduce_weights(const float* dmin, int64_t Mq, int nb_img, int Pq, const i
  * i.e. the distance of patch (j,c) to its nearest patch of image i.  Values are SQUARED distances; entries of
  * pairs that are not owned are undefined (rowmin) / huge (colmin).  With a single rank (Mq = nb_img*P) colmin is
  * already laid out as [bank image, query row]; sharded runs exchange column blocks (all-to-all) first.
+ * Only bank images in the circular window [bank_begin, bank_begin + bank_count) are visited (bank_count = nb_img:
+ * all), so a sharded run can multiply against its local shard while the remote shards are still in flight and
+ * finish with a second call; init_colmin = 1 resets colmin first (first call of a sequence).
  * Tensor-core precisions only; needs P >= 32 and Mq % P == 0, else AC_ERR_UNSUPPORTED (use ac_min_dist). */
 int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
-                    const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, float* rowmin_d2,
-                    float* colmin_d2, void* ws, size_t ws_bytes, ac_stream_t stream);
+                    const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                    int bank_count, int init_colmin, float* rowmin_d2, float* colmin_d2, void* ws, size_t ws_bytes,
+                    ac_stream_t stream);
 
 /* w[r] = mean over bank images j != i(r) of sqrt(owned(i,j) ? rowmin_d2[j,r] : colmin_d2[j,r]); both arrays
  * [nb_img, Mq], i(r) = q_img0 + r / Pq.  Replaces utils.py:227 for the symmetric form. */

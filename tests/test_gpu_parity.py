@@ -248,6 +248,29 @@ def test_mindist_symmetric_sharded_slices():
         assert ((w - w_one[a:b]).abs() / w_one[a:b]).max().item() <= 2e-4
 
 
+def test_mindist_symmetric_bank_windows_accumulate():
+    """Two launches over complementary circular windows of bank images (what the sharded path does to overlap
+    the shard transfers) give bit-identical minima to one launch."""
+    n, P, D = 9, 64, 128
+    gen = torch.Generator().manual_seed(11)
+    Z = (torch.randn(1, P, D, generator=gen) + 0.5 * torch.randn(n, P, D, generator=gen)).cuda()
+    ps = pipeline.patchset_from_Z(Z, "f16")
+    a, b = 3, 6                                   # this "rank" owns query images [3, 6)
+    sl = slice(a * P, b * P)
+    one = ops.min_dist_sym(ps.hi[sl], None, ps.n2[sl], a, ps.hi, None, ps.n2, n, P, "f16")
+    two = ops.min_dist_sym(ps.hi[sl], None, ps.n2[sl], a, ps.hi, None, ps.n2, n, P, "f16", bank_window=(a, b - a), init=True)
+    two = ops.min_dist_sym(ps.hi[sl], None, ps.n2[sl], a, ps.hi, None, ps.n2, n, P, "f16", bank_window=(b % n, n - (b - a)),
+                           init=False, out=two)
+    from anomaly_clustering_b200 import distributed
+
+    assert torch.equal(one[1], two[1])                       # column minima: every entry
+    for j in range(n):                                       # row minima: only owned pairs are defined
+        for i in range(a, b):
+            if distributed.pair_owned(i, j, n):
+                r = slice((i - a) * P, (i - a + 1) * P)
+                assert torch.equal(one[0][j, r], two[0][j, r])
+
+
 # ------------------------------------------------------------------------------- stage 3
 def test_alpha_golden(golden_dir):
     g = gload(golden_dir, "alpha_small")
