@@ -130,6 +130,26 @@ def start_gather_needed_rows(local: torch.Tensor, bounds: Sequence[Tuple[int, in
     return buf, reqs
 
 
+def start_all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None):
+    """Asynchronous all-gather of row blocks into one buffer whose local slice is already valid, so work on
+    the local shard can overlap the collective.  Returns (buffer, [work])."""
+    rank = dist.get_rank(group)
+    tail = tuple(local.shape[1:])
+    local = local.contiguous()
+    buf = torch.empty((sum(counts),) + tail, dtype=local.dtype, device=local.device)
+    start = sum(counts[:rank])
+    buf[start:start + counts[rank]].copy_(local)
+    if all(c == counts[0] for c in counts):
+        work = dist.all_gather_into_tensor(buf, local, group=group, async_op=True)
+    else:
+        views, s0 = [], 0
+        for c in counts:
+            views.append(buf[s0:s0 + c])
+            s0 += c
+        work = dist.all_gather(views, local, group=group, async_op=True)
+    return buf, [work]
+
+
 def gather_needed_rows(local, bounds, rows_per_item, need, group=None) -> torch.Tensor:
     buf, reqs = start_gather_needed_rows(local, bounds, rows_per_item, need, group)
     for r in reqs:
@@ -210,10 +230,18 @@ def run_path_sharded(
     if use_sym:
         # only the shards that hold bank images of pairs this rank owns (the next n_total//2 images);
         # the transfers stay in flight while the pairs inside the local shard are multiplied
-        need = needed_shards(bounds, n_total)
-        hi_buf, r1 = start_gather_needed_rows(q.hi, bounds, P, need, group)
-        lo_buf, r2 = (None, []) if q.lo is None else start_gather_needed_rows(q.lo, bounds, P, need, group)
-        n2_buf, r3 = start_gather_needed_rows(q.n2, bounds, P, need, group)
+        if world <= 4 or dist.get_backend(group) != "nccl":
+            # few ranks: point-to-point transfers of just the needed shards (about half the volume)
+            need = needed_shards(bounds, n_total)
+            hi_buf, r1 = start_gather_needed_rows(q.hi, bounds, P, need, group)
+            lo_buf, r2 = (None, []) if q.lo is None else start_gather_needed_rows(q.lo, bounds, P, need, group)
+            n2_buf, r3 = start_gather_needed_rows(q.n2, bounds, P, need, group)
+        else:
+            # many ranks: NCCL's all-gather moves the whole bank faster than 4+ send/recv pairs per rank
+            # move half of it (measured at 8 GPUs: 562 MB in 1.0 ms vs 321 MB in 1.2 ms)
+            hi_buf, r1 = start_all_gather_rows(q.hi, row_counts, group)
+            lo_buf, r2 = (None, []) if q.lo is None else start_all_gather_rows(q.lo, row_counts, group)
+            n2_buf, r3 = start_all_gather_rows(q.n2, row_counts, group)
         pending = list(r1) + list(r2) + list(r3)
         bank = pipeline.PatchSet(n_total, P, q.D, q.grid, hi=hi_buf, lo=lo_buf, n2=n2_buf)
     elif precision == "f32":
