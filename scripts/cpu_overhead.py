@@ -41,16 +41,14 @@ torch.cuda.synchronize()
 t2 = time.perf_counter()
 if rank == 0:
     print("world=%d: host enqueue %.3f ms/step, wall incl. drain %.3f ms/step" % (world, (t1 - t0) / 50 * 1e3, (t2 - t0) / 50 * 1e3))
-    pr = cProfile.Profile() if world == 1 else None
-    if pr is None:
-        raise SystemExit(0)
+if world == 1:   # cProfile only single-process: every rank must execute the same collectives
+    pr = cProfile.Profile()
     pr.enable()
     for _ in range(50):
         step()
     pr.disable()
     torch.cuda.synchronize()
-    st = pstats.Stats(pr)
-    st.sort_stats("cumulative").print_stats(28)
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
