@@ -519,8 +519,7 @@ __device__ __forceinline__ bool unit_has_work(const TcParams& p, int G, int mb, 
   return false;
 }
 
-__global__ void __launch_bounds__(1024) build_units_kernel(TcParams p, int G, int2* units, long long* n_units, int* err_flag,
-                                                           unsigned int* colmin, long long colmin_words) {
+__global__ void __launch_bounds__(1024) build_units_kernel(TcParams p, int G, int2* units, long long* n_units, int* err_flag) {
   __shared__ long long s_scan[1024];
   const int tid = threadIdx.x;
   if (tid == 0 && err_flag) *err_flag = 0;
@@ -561,7 +560,6 @@ __global__ void __launch_bounds__(1024) build_units_kernel(TcParams p, int G, in
       if (unit_has_work(p, G, mb, img)) units[pos++] = make_int2(mb, img);
     }
   }
-  (void)colmin; (void)colmin_words;
 }
 
 // grid-stride fill (SM-side replacement of cudaMemsetAsync: keeps the launch sequence off the copy engines)
@@ -610,7 +608,7 @@ static uint32_t make_idesc(int M, int N, bool bf16) {
 }
 
 static int g_tc_cta_group = 2;   // test hook (ac_debug_set): 1 = single-CTA MMAs, 2 = CTA pairs
-static int g_tc_l2hint = 0;  // debug knob 3
+static int g_tc_l2hint = 0;  // debug knob 3: L2 evict_last policy on operand loads (measured: no gain, off)
 static int g_tc_gm = 16;  // query blocks per raster group: 16 x 2 MB of A + the streaming bank images stay L2-resident (tuned on B200)
 
 template <int G, int kStages>
@@ -676,7 +674,7 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
     if (!unit_ws || unit_ws_bytes < 16 + (size_t)max_units * sizeof(int2)) return AC_ERR_WORKSPACE;
     long long* d_n = (long long*)unit_ws;
     int2* d_units = (int2*)((char*)unit_ws + 16);
-    build_units_kernel<<<1, 1024, 0, st>>>(prm, G, d_units, d_n, err_flag, nullptr, 0);
+    build_units_kernel<<<1, 1024, 0, st>>>(prm, G, d_units, d_n, err_flag);
     AC_LAUNCH_CHECK();
     prm.units = d_units;
     prm.n_units = d_n;
