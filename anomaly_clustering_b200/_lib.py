@@ -73,6 +73,12 @@ SIGNATURES = {
     "ac_reduce_weights": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ac_alpha": (c_int, [c_void_p, c_int, c_int, POINTER(c_double), c_int, c_void_p, c_void_p, c_void_p]),
     "ac_weighted_embed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ac_weighted_embed_from_features_workspace_bytes": (c_size_t, [POINTER(AcLayer), c_int, c_int, c_int]),
+    "ac_weighted_embed_from_features": (
+        c_int,
+        [POINTER(AcLayer), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+         c_void_p],
+    ),
     "ac_pairwise_l2": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 

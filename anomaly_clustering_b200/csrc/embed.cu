@@ -781,6 +781,79 @@ __global__ void __launch_bounds__(256) upsample_store_kernel(EmbedParams p, cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// X straight from the feature maps.  Z is a fixed linear map of the LayerNorm'd
+// maps, so  X_i = sum_p alpha_ip Z_ip = Pool( A_i ),  A_i[c,ki,kj] = sum_p alpha_ip * LN_i[c, y_p+ki-pad, x_p+kj-pad]
+// (zero outside the map): a k x k correlation of the alpha map with every channel, then the SAME two pooling
+// windows applied once per image instead of once per patch.  fp32 Z never has to exist.
+//   xcorr_kernel : partial A over a slice of rows; thread = channel (coalesced), alpha map with a zero halo in smem
+//   xpool_kernel : X[i,t] = sum over taps of wt * (sum of partials)
+static constexpr int kXSplit = 4;
+
+template <int K>
+__global__ void __launch_bounds__(256) xcorr_kernel(EmbedParams p, int layer, const float* __restrict__ alpha /*[B, P0]*/,
+                                                    float* __restrict__ part /*[B, kXSplit, K*K, C]*/) {
+  extern __shared__ float s_alpha[];   // (h0 + 2*pad) x (w0 + 2*pad), zero halo
+  __shared__ float s_mu, s_rstd;
+  const LayerDev ly = p.layers[layer];
+  const int b = blockIdx.z, split = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int aw = p.w0 + 2 * p.pad, ah = p.h0 + 2 * p.pad;
+  for (int e = threadIdx.x; e < aw * ah; e += blockDim.x) {
+    const int y = e / aw - p.pad, x = e % aw - p.pad;
+    s_alpha[e] = (y >= 0 && y < p.h0 && x >= 0 && x < p.w0) ? alpha[(long long)b * p.h0 * p.w0 + y * p.w0 + x] : 0.f;
+  }
+  if (threadIdx.x < 32) {
+    float mu, rstd;
+    warp_ln_params(p, ly, p.b0 + b, layer, lane, mu, rstd);
+    if (lane == 0) { s_mu = mu; s_rstd = rstd; }
+  }
+  __syncthreads();
+  if (c >= ly.C) return;
+  const float mu = s_mu, rstd = s_rstd;
+  float acc[K][K];
+#pragma unroll
+  for (int ki = 0; ki < K; ++ki)
+#pragma unroll
+    for (int kj = 0; kj < K; ++kj) acc[ki][kj] = 0.f;
+  const int y0 = (int)((long long)ly.H * split / kXSplit), y1 = (int)((long long)ly.H * (split + 1) / kXSplit);
+  const float* src = ly.ptr + (long long)(p.b0 + b) * ly.sb + (long long)c * ly.sc;
+  for (int iy = y0; iy < y1; ++iy)
+    for (int ix = 0; ix < ly.W; ++ix) {
+      const float v = (__ldg(src + (long long)iy * ly.sh + (long long)ix * ly.sw) - mu) * rstd;
+      // input (iy, ix) is tap (ki, kj) of output position (iy - ki + pad, ix - kj + pad); s_alpha is offset by pad
+      const float* a = s_alpha + (iy + 2 * p.pad) * aw + (ix + 2 * p.pad);
+#pragma unroll
+      for (int ki = 0; ki < K; ++ki)
+#pragma unroll
+        for (int kj = 0; kj < K; ++kj) acc[ki][kj] = fmaf(a[-ki * aw - kj], v, acc[ki][kj]);
+    }
+  float* out = part + (((long long)b * kXSplit + split) * K * K) * ly.C + c;
+#pragma unroll
+  for (int ki = 0; ki < K; ++ki)
+#pragma unroll
+    for (int kj = 0; kj < K; ++kj) out[(long long)(ki * K + kj) * ly.C] = acc[ki][kj];
+}
+
+__global__ void __launch_bounds__(256) xpool_kernel(EmbedParams p, int layer, int t_begin, int t_end, const float* __restrict__ part,
+                                                    float* __restrict__ X /*[B, D]*/) {
+  const LayerDev ly = p.layers[layer];
+  const int b = blockIdx.y;
+  const int t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= t_end) return;
+  const int kk = p.k * p.k;
+  float acc = 0.f;
+  for_each_tap(t, p.agg_in, p.agg_out, p.Dp, ly.CK, [&](int f, float w) {
+    const int c = f / kk, tap = f - c * kk;
+    float sacc = 0.f;
+    for (int sp = 0; sp < kXSplit; ++sp) sacc += __ldg(part + (((long long)b * kXSplit + sp) * kk + tap) * ly.C + c);
+    acc = fmaf(w, sacc, acc);
+  });
+  X[(long long)(p.b0 + b) * p.agg_out + t] = acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // standalone compat kernels
 __global__ void patchify_kernel(const float* __restrict__ x, int B, int C, int H, int W, int k, int s, int pad,
@@ -1321,6 +1394,66 @@ extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, i
 extern "C" int ac_debug_set_embed(int value) {
   if (value < 0 || value > 2) return AC_ERR_INVALID;
   g_embed_variant = value;
+  return AC_OK;
+}
+
+extern "C" size_t ac_weighted_embed_from_features_workspace_bytes(const ac_layer_t* layers, int L, int B, int patchsize) {
+  if (!layers || L < 1 || L > kMaxLayers || B < 1 || patchsize < 1) return 0;
+  size_t stats = align256((size_t)B * L * kStatSplit * 2 * sizeof(double));
+  size_t part = 0;
+  for (int l = 0; l < L; ++l) part = std::max(part, align256((size_t)B * kXSplit * patchsize * patchsize * layers[l].C * sizeof(float)));
+  return stats + part;
+}
+
+extern "C" int ac_weighted_embed_from_features(const ac_layer_t* layers, int L, int B, int patchsize, int stride, int Dp, int D,
+                                               int layernorm, float eps, const float* alpha, float* X, void* ws, size_t ws_bytes,
+                                               ac_stream_t stream) {
+  if (!layers || !alpha || !X || !ws || B < 1) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::shared_ptr<Plan> plan_sp;
+  rc = get_plan(layers, L, patchsize, stride, Dp, D, layernorm, eps, plan_sp);
+  if (rc) return rc;
+  const Plan& plan = *plan_sp;
+  if (!plan.fused || patchsize != 3 || stride != 1) return AC_ERR_UNSUPPORTED;   // Aggregator windows inside one layer, 3x3 patches
+  EmbedParams p = plan.p;
+  p.eps = eps;
+  for (int l = 0; l < L; ++l) {
+    if (!layers[l].ptr) return AC_ERR_INVALID;
+    if (p.layers[l].resample) return AC_ERR_UNSUPPORTED;                          // all layers on the layer-0 grid
+    p.layers[l].ptr = layers[l].ptr;
+    p.layers[l].sb = layers[l].sb;
+  }
+  const size_t need = ac_weighted_embed_from_features_workspace_bytes(layers, L, B, patchsize);
+  if (ws_bytes < need) return AC_ERR_WORKSPACE;
+  const size_t stats_b = align256((size_t)B * L * kStatSplit * 2 * sizeof(double));
+  double* dstats = (double*)ws;
+  float* part = (float*)((char*)ws + stats_b);
+  p.stats = dstats;
+  const int nb = std::min(B, 65535);
+  const size_t smem = (size_t)(p.h0 + 2 * p.pad) * (p.w0 + 2 * p.pad) * sizeof(float);
+  if (smem > 200 * 1024) return AC_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) AC_CUDA(cudaFuncSetAttribute(xcorr_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int b0 = 0; b0 < B; b0 += nb) {
+    p.b0 = b0;
+    p.B = std::min(nb, B - b0);
+    if (layernorm) {
+      ln_stats_kernel<<<dim3(kStatSplit, L, p.B), 256, 0, st>>>(p, dstats);
+      AC_LAUNCH_CHECK();
+    }
+    for (int l = 0; l < L; ++l) {
+      // output columns owned by layer l (fused Aggregator: contiguous range)
+      int ta = -1, tb = -1;
+      for (int t = 0; t < p.agg_out; ++t)
+        if (pool_start(t, p.agg_in, p.agg_out) / Dp == l) { if (ta < 0) ta = t; tb = t + 1; }
+      if (ta < 0) continue;
+      xcorr_kernel<3><<<dim3(ceil_div(p.layers[l].C, 256), kXSplit, p.B), 256, smem, st>>>(p, l, alpha + (long long)b0 * p.h0 * p.w0, part);
+      AC_LAUNCH_CHECK();
+      xpool_kernel<<<dim3(ceil_div(tb - ta, 256), p.B), 256, 0, st>>>(p, l, ta, tb, part, X);
+      AC_LAUNCH_CHECK();
+    }
+  }
   return AC_OK;
 }
 

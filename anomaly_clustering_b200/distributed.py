@@ -192,6 +192,7 @@ def run_path_sharded(
     group=None,
     compute=None,
     symmetric: bool = True,
+    keep_z: bool = True,
 ):
     """Unsupervised path over n_total images sharded by shard_bounds(); `local_features` are this
     rank's images.  Returns (alpha64_local [T,n_r,P], X_all [T,N,D], Dmat [T,N,N], w_local).
@@ -213,6 +214,7 @@ def run_path_sharded(
             pairwise_l2 = staticmethod(ops.pairwise_l2)
             min_dist_sym = staticmethod(ops.min_dist_sym)
             supports_bank_window = True
+            weighted_embed_from_features = staticmethod(ops.weighted_embed_from_features)
             reduce_weights_sym = staticmethod(ops.reduce_weights_sym)
 
         compute = _Cuda
@@ -220,7 +222,9 @@ def run_path_sharded(
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     bounds = shard_bounds(n_total, world)
     lo_i, hi_i = bounds[rank]
-    q = compute.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=True)
+    z_free = (not keep_z) and hasattr(compute, "weighted_embed_from_features") and pipeline.z_free_supported(
+        local_features, patchsize, stride, pretrain_dim, target_dim, precision)
+    q = compute.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=not z_free)
     assert q.n_img == hi_i - lo_i
     P = q.P
     row_counts = [(b - a) * P for a, b in bounds]
@@ -281,11 +285,15 @@ def run_path_sharded(
         pipeline._mark("exchange_end")
         w = compute.reduce_weights_sym(rowmin, colfull, P, lo_i).reshape(q.n_img, P)
     else:
-        q_self = torch.arange(lo_i, hi_i, dtype=torch.int32, device=q.Z.device)
+        q_self = torch.arange(lo_i, hi_i, dtype=torch.int32, device=q.hi.device if q.Z is None else q.Z.device)
         w = compute.min_distance_weights(q, bank, "unsupervised", precision, q_self=q_self)
     a64, a32 = compute.alpha(w, list(taus))
-    Z3 = q.Z.reshape(q.n_img, P, q.D)
-    X_loc = torch.stack([compute.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)  # [n_r, T, D]
+    if z_free:
+        X_loc = torch.stack([compute.weighted_embed_from_features(local_features, a32[t], patchsize, stride, pretrain_dim, q.D)
+                             for t in range(len(taus))], dim=1)
+    else:
+        Z3 = q.Z.reshape(q.n_img, P, q.D)
+        X_loc = torch.stack([compute.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)  # [n_r, T, D]
     pipeline._mark("xgather_begin")
     X_all = all_gather_rows(X_loc, [b - a for a, b in bounds], group).permute(1, 0, 2).contiguous()  # [T, N, D]
     pipeline._mark("xgather_end")

@@ -238,6 +238,36 @@ def weighted_embed(alpha32: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
     return X
 
 
+def _layer_array(features):
+    views = [feature_view(f) for f in features]
+    _need_cuda(*views)
+    arr = (AcLayer * len(views))()
+    for i, v in enumerate(views):
+        if v.dtype != torch.float32:
+            raise ValueError("features must be float32")
+        _, C, H, W = v.shape
+        sb, sc, sh, sw = v.stride()
+        arr[i] = AcLayer(v.data_ptr(), C, H, W, sb, sc, sh, sw)
+    return views, arr
+
+
+def weighted_embed_from_features(features: Sequence[torch.Tensor], alpha32: torch.Tensor, patchsize: int, stride: int,
+                                 pretrain_dim: int, target_dim: int, layernorm: bool = True, eps: float = 1e-5) -> torch.Tensor:
+    """X [B, D] = sum_p alpha[b,p] Z[b,p] computed from the feature maps (no Z).  Raises AcError(AC_ERR_UNSUPPORTED)
+    for shapes outside the fast form (callers fall back to embed + weighted_embed)."""
+    lib = _lib.load()
+    views, arr = _layer_array(features)
+    B, L = views[0].shape[0], len(views)
+    a = alpha32.reshape(B, -1).contiguous().float()
+    X = torch.empty(B, target_dim, dtype=torch.float32, device=views[0].device)
+    ws_bytes = lib.ac_weighted_embed_from_features_workspace_bytes(arr, L, B, patchsize)
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=views[0].device)
+    rc = lib.ac_weighted_embed_from_features(arr, L, B, patchsize, stride, pretrain_dim, target_dim, int(layernorm), float(eps),
+                                             _ptr(a), _ptr(X), _ptr(ws), ws_bytes, _stream())
+    check(rc, "ac_weighted_embed_from_features")
+    return X
+
+
 def pairwise_l2(X: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     _need_cuda(X)

@@ -64,7 +64,7 @@ class PatchSet:
 
 @dataclass
 class PathResult:
-    Z: torch.Tensor                       # [N, P, D] fp32
+    Z: Optional[torch.Tensor]             # [N, P, D] fp32 (None when run with keep_z=False)
     w: Optional[torch.Tensor]             # [N, P] fp32 (None in 'average' mode)
     alpha64: torch.Tensor                 # [T, N, P] float64  (reference dtype, utils.py:246)
     alpha32: torch.Tensor                 # [T, N, P] float32  (main.py:294 `.float()`)
@@ -164,20 +164,39 @@ def min_distance_weights(
     return (w, dmin) if return_dmin else w
 
 
-def alpha_X_dist(ps: PatchSet, w: Optional[torch.Tensor], taus: Sequence[float]):
-    """Stage 3 for every tau from one w.  w=None -> 'average' mode (main.py:290-291)."""
+def alpha_X_dist(ps: PatchSet, w: Optional[torch.Tensor], taus: Sequence[float], features=None, embed_args=None):
+    """Stage 3 for every tau from one w.  w=None -> 'average' mode (main.py:290-291).
+    When the PatchSet carries no fp32 Z, X is computed straight from `features` (ac_weighted_embed_from_features)."""
     N, P, D = ps.n_img, ps.P, ps.D
-    dev = ps.Z.device
+    dev = (ps.Z if ps.Z is not None else ps.hi).device
     if w is None:
         a32 = torch.full((1, N, P), 1.0 / P, dtype=torch.float32, device=dev)
         a64 = a32.double()
         taus = [float("nan")]
     else:
         a64, a32 = ops.alpha(w, taus)
-    Z3 = ps.Z.reshape(N, P, D)
-    X = torch.stack([ops.weighted_embed(a32[t], Z3) for t in range(a32.shape[0])])
+    if ps.Z is not None:
+        Z3 = ps.Z.reshape(N, P, D)
+        X = torch.stack([ops.weighted_embed(a32[t], Z3) for t in range(a32.shape[0])])
+    else:
+        patchsize, stride, Dp, layernorm = embed_args
+        X = torch.stack([ops.weighted_embed_from_features(features, a32[t], patchsize, stride, Dp, D, layernorm=layernorm)
+                         for t in range(a32.shape[0])])
     Dm = torch.stack([ops.pairwise_l2(X[t]) for t in range(a32.shape[0])])
     return a64, a32, X, Dm
+
+
+def z_free_supported(features, patchsize, stride, pretrain_dim, target_dim, precision) -> bool:
+    """Shapes covered by ac_weighted_embed_from_features (see include/ac_b200.h)."""
+    if precision == "f32" or patchsize != 3 or stride != 1:
+        return False
+    views = [ops.feature_view(f) for f in features]
+    if any(v.shape[2:] != views[0].shape[2:] for v in views):
+        return False
+    L = len(views)
+    if (L * pretrain_dim) % target_dim != 0 or pretrain_dim % ((L * pretrain_dim) // target_dim) != 0:
+        return False
+    return True
 
 
 def run_path(
@@ -191,10 +210,16 @@ def run_path(
     bank_features: Optional[Sequence[torch.Tensor]] = None,
     precision: str = "auto",
     layernorm: bool = True,
+    keep_z: bool = True,
 ) -> PathResult:
-    """Single-GPU hot path: hooked features (device tensors) -> PathResult (device tensors)."""
+    """Single-GPU hot path: hooked features (device tensors) -> PathResult (device tensors).
+    keep_z=False never materialises the fp32 Z (1.3 GB at config 2): the embed kernel writes only the
+    tensor-core operands and X comes straight from the feature maps; falls back to keep_z=True for shapes the
+    Z-free form does not cover (resampled layers, patch size != 3, fp32 precision)."""
     precision = resolve_precision(precision, taus)
-    q = embed_images(features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=True, layernorm=layernorm)
+    if not keep_z and not z_free_supported(features, patchsize, stride, pretrain_dim, target_dim, precision):
+        keep_z = True
+    q = embed_images(features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=keep_z, layernorm=layernorm)
     w = None
     if mode == "unsupervised":
         w = min_distance_weights(q, q, "unsupervised", precision)
@@ -206,6 +231,6 @@ def run_path(
         w = min_distance_weights(q, bank, "supervised", precision)
     elif mode != "average":
         raise ValueError("mode must be unsupervised | supervised | average")
-    a64, a32, X, Dm = alpha_X_dist(q, w, list(taus))
-    return PathResult(Z=q.Z.reshape(q.n_img, q.P, q.D), w=w, alpha64=a64, alpha32=a32, X=X, Dmat=Dm,
+    a64, a32, X, Dm = alpha_X_dist(q, w, list(taus), features, (patchsize, stride, pretrain_dim, layernorm))
+    return PathResult(Z=None if q.Z is None else q.Z.reshape(q.n_img, q.P, q.D), w=w, alpha64=a64, alpha32=a32, X=X, Dmat=Dm,
                       taus=list(taus), grid=q.grid)

@@ -167,6 +167,17 @@ int ac_alpha(const float* w, int N, int P, const double* taus_host, int T, doubl
 int ac_weighted_embed(const float* alpha, const float* Z, int N, int P, int D, float* X,
                       ac_stream_t stream);
 
+/* X without Z: Z is a fixed linear map of the LayerNorm'd feature maps, so
+ * X[i] = sum_p alpha[i,p] Z[i,p] = Pool(A_i) with A_i[c,ki,kj] = sum_p alpha[i,p] * LN_i[c, y_p+ki-1, x_p+kj-1]:
+ * a 3x3 correlation of the alpha map with every channel, then the MeanMapper / Aggregator windows once per
+ * image.  Same result as ac_embed + ac_weighted_embed (examples/main.py:266-296) while fp32 Z is never stored.
+ * alpha [B, P] fp32, X [B, D] fp32.  Needs patchsize 3, stride 1, every layer on the layer-0 grid and Aggregator
+ * windows that do not straddle layers, else AC_ERR_UNSUPPORTED (use ac_embed + ac_weighted_embed). */
+size_t ac_weighted_embed_from_features_workspace_bytes(const ac_layer_t* layers_host, int L, int B, int patchsize);
+int ac_weighted_embed_from_features(const ac_layer_t* layers_host, int L, int B, int patchsize, int stride, int Dp,
+                                    int D, int layernorm, float eps, const float* alpha, float* X, void* ws,
+                                    size_t ws_bytes, ac_stream_t stream);
+
 /* Dmat[i,j] = || X[i] - X[j] ||_2, the Euclidean matrix Ward linkage consumes
  * (examples/test.py:193-195 -> scipy pdist).  Dmat [N,N] fp32, exactly symmetric, zero diagonal. */
 int ac_pairwise_l2(const float* X, int N, int D, float* Dmat, ac_stream_t stream);

@@ -363,6 +363,31 @@ def test_full_path_supervised_and_average_vit_shape():
     _check_path(res_avg, want_avg, labels.numpy(), k)
 
 
+@pytest.mark.parametrize("layers,Dp,D", [([(768, 28, 28, True), (768, 28, 28, True)], 2048, 4096),
+                                         ([(64, 12, 12, False), (64, 12, 12, False)], 128, 128),
+                                         ([(96, 10, 14, True)], 256, 256)])
+def test_z_free_path_matches_z_path(layers, Dp, D):
+    """keep_z=False (operands only from the embed kernel, X as a 3x3 correlation of alpha with the feature maps)
+    against the Z-based path and the oracle."""
+    tokens = layers[0][3]
+    if tokens and layers[0][1] != layers[0][2]:
+        layers = [(c, 12, 12, t) for c, _, _, t in layers]
+    feats, _ = synth.planted_features(4, layers, seed=21)
+    f = [x.cuda() for x in feats]
+    a = pipeline.run_path(f, 3, 1, Dp, D, "unsupervised", [1.0, 2.0], precision="f16", keep_z=True)
+    b = pipeline.run_path(f, 3, 1, Dp, D, "unsupervised", [1.0, 2.0], precision="f16", keep_z=False)
+    assert b.Z is None and a.Z is not None
+    assert torch.equal(a.w, b.w) and torch.equal(a.alpha64, b.alpha64)
+    assert ((a.X - b.X).norm() / a.X.norm()).item() <= 1e-5
+    want = restated.full_path(feats, 3, 1, Dp, D, 2.0, "unsupervised")
+    assert rel_l2(b.X[1].cpu().numpy(), want[3]) <= 1e-3
+    assert rel_l2(b.Dmat[1].cpu().numpy(), want[4]) <= 1e-3
+    # average mode without Z
+    c = pipeline.run_path(f, 3, 1, Dp, D, "average", keep_z=False)
+    want_avg = restated.full_path(feats, 3, 1, Dp, D, 1.0, "average")
+    assert rel_l2(c.X[0].cpu().numpy(), want_avg[3]) <= 1e-4
+
+
 def test_tau_sweep_reuses_one_distance_pass():
     """Config 5 behaviour: every tau from one min-distance pass equals per-tau runs."""
     feats, _ = synth.planted_features(5, [(96, 12, 12, True), (96, 12, 12, True)], seed=4)
