@@ -173,7 +173,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2, help="query images per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--keep-z", action="store_true", help="materialise the fp32 Z (1.3 GB at config 2) and compute X from it")
+    ap.add_argument("--z-free", action="store_true",
+                    help="never materialise the fp32 Z (1.3 GB at config 2): operands only from the embed kernel, X from the feature maps")
     ap.add_argument("--no-symmetry", action="store_true", help="force the all-pairs distance kernel (every image pair multiplied twice)")
     ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -219,10 +220,10 @@ def main():
 
     def step(f):
         if world == 1:
-            r = pipeline.run_path(f, 3, 1, Dp, D, "unsupervised", [tau], precision=args.precision, keep_z=args.keep_z)
+            r = pipeline.run_path(f, 3, 1, Dp, D, "unsupervised", [tau], precision=args.precision, keep_z=not args.z_free)
             return r.alpha32, r.X, r.Dmat
         a64, X, Dm, _ = distributed.run_path_sharded(f, n_img, 3, 1, Dp, D, [tau], precision=args.precision, symmetric=symmetric,
-                                                     keep_z=args.keep_z)
+                                                     keep_z=not args.z_free)
         return a64, X, Dm
 
     def sync_all():
@@ -283,7 +284,7 @@ def main():
         exec_flops = flops
     tflops = exec_flops / (md_ms * 1e-3) / 1e12 if md_ms > 0 else 0.0
     alg_tflops = flops / (md_ms * 1e-3) / 1e12 if md_ms > 0 else 0.0
-    z_free = (not args.keep_z) and pipeline.z_free_supported(feats, 3, 1, Dp, D, args.precision)
+    z_free = args.z_free and pipeline.z_free_supported(feats, 3, 1, Dp, D, args.precision)
     embed_bytes = nq_local * (sum(c * h * w * 4 for c, h, w, _ in layers) + (0 if z_free else P * D * 4)
                               + (P * D * 2 if args.precision != "f32" else 0))
     embed_gbs = embed_bytes / (emb_ms * 1e-3) / 1e9 if emb_ms > 0 else 0.0
