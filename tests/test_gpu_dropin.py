@@ -92,3 +92,17 @@ def test_make_category_data_vit_writes_reference_pickle(tmp_path):
         a_l, X_l = io.load_matrix_alpha_X(str(tmp_path / ("blocks.10_blocks.11_512_1024_%s_1.0" % float(tau))
                                               / "matrix_alpha_X_bottle_unsupervised.pickle"))
         assert np.array_equal(X_l, X) and torch.equal(a_l, alpha.cpu())
+
+
+def test_cli_synthetic_run(tmp_path):
+    """python -m anomaly_clustering_b200.main with the reference's argument names (WRN50 config-1 shape)."""
+    import os
+
+    from anomaly_clustering_b200 import main as cli
+
+    rows = cli.main(["--dataset", "synthetic", "--backbone_names", "wideresnet50", "--layers_to_extract_from", "layer2", "layer3",
+                     "--pretrain_embed_dimension", "1024", "--target_embed_dimension", "1024", "--tau", "1", "2",
+                     "--synthetic_images", "8", "--synthetic_classes", "2", "--output_dir", str(tmp_path)])
+    assert len(rows) == 2 and all(0.0 <= r[2] <= 1.0 for r in rows)
+    p = tmp_path / "synthetic" / "wideresnet50" / "unsupervised" / "layer2_layer3_1024_1024_2.0_1.0" / "matrix_alpha_X_bottle_unsupervised.pickle"
+    assert os.path.exists(p)
