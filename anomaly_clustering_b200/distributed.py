@@ -261,7 +261,10 @@ def run_path_sharded(
     if use_sym:
         # every unordered image pair is multiplied once, by the rank that owns the pair's first image;
         # the column minima it produces for other ranks' query rows travel in one small all-to-all
-        two_phase = bool(pending) and q.n_img > 1 and getattr(compute, "supports_bank_window", False)
+        # Overlap pays once the local shard is a small part of the work: NCCL's transfer kernels take SMs
+        # away from the persistent GEMM (statically scheduled over all SMs), which costs more than the hidden
+        # transfer at 2 ranks (measured 11.6 vs 10.1 ms per step) and less from 4 ranks on (5.5 vs 5.8 ms).
+        two_phase = bool(pending) and q.n_img > 1 and world >= 3 and getattr(compute, "supports_bank_window", False)
         if two_phase:
             # phase 1: bank images of the local shard (no remote data needed) overlaps the NCCL transfers
             pipeline._mark("mindist_begin")
