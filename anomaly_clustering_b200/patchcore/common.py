@@ -49,18 +49,18 @@ class LastLayerToExtractReachedException(Exception):
 
 
 class ForwardHook:
-    """common.py:277-289 -- stores the hooked module output under `layer_name`."""
+    """common.py:277-289 -- forward hook that files the module output under `layer_name` and, on the
+    deepest requested layer, aborts the rest of the backbone forward."""
 
     def __init__(self, hook_dict, layer_name: str, last_layer_to_extract: str):
         self.hook_dict = hook_dict
         self.layer_name = layer_name
-        self.raise_exception_to_break = layer_name == last_layer_to_extract
+        self.is_last = layer_name == last_layer_to_extract
 
-    def __call__(self, module, input, output):
+    def __call__(self, module, inputs, output):
         self.hook_dict[self.layer_name] = output
-        if self.raise_exception_to_break:
+        if self.is_last:
             raise LastLayerToExtractReachedException()
-        return None
 
 
 class NetworkFeatureAggregator(torch.nn.Module):

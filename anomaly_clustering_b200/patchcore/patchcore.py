@@ -29,15 +29,15 @@ class PatchMaker:
         return unfolded
 
     def unpatch_scores(self, x, batchsize):
+        """[B*P, ...] -> [B, P, ...] (patchcore.py:467-468)."""
         return x.reshape(batchsize, -1, *x.shape[1:])
 
     def score(self, x):
-        was_numpy = isinstance(x, np.ndarray)
-        if was_numpy:
-            x = torch.from_numpy(x)
-        while x.ndim > 1:
-            x = torch.max(x, dim=-1).values
-        return x.numpy() if was_numpy else x
+        """Max over all trailing axes, numpy in -> numpy out (patchcore.py:470-481)."""
+        t = torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+        if t.ndim > 1:
+            t = t.reshape(t.shape[0], -1).max(dim=1).values
+        return t.numpy() if isinstance(x, np.ndarray) else t
 
 
 class AnomalyClusteringCore(torch.nn.Module):
@@ -82,23 +82,19 @@ class AnomalyClusteringCore(torch.nn.Module):
                          self.target_embed_dimension, layernorm=True, operand=operand, want_lo=want_lo)
 
     def embed(self, data, supervised):
-        """patchcore.py:337-353."""
+        """patchcore.py:337-353 -- a DataLoader yields per-batch embeddings + the `is_anomaly` labels,
+        anything else is embedded directly.  (`supervised` is accepted and unused, as in the reference.)"""
         print("{:-^80}".format("embedding"))
-        if isinstance(data, torch.utils.data.DataLoader):
-            features, labels = [], []
-            with tqdm.tqdm(total=len(data)) as progress:
-                for image in data:
-                    is_anomaly = None
-                    if isinstance(image, dict):
-                        is_anomaly = image["is_anomaly"]
-                        image = image["image"]
-                    with torch.no_grad():
-                        input_image = image.to(torch.float).to(self.device)
-                        features.append(self._embed(input_image, supervised))
-                        labels.append(is_anomaly)
-                    progress.update(1)
-            return features, labels
-        return self._embed(data, supervised)
+        if not isinstance(data, torch.utils.data.DataLoader):
+            return self._embed(data, supervised)
+        per_batch, flags = [], []
+        for batch in tqdm.tqdm(data, total=len(data)):
+            flag = batch["is_anomaly"] if isinstance(batch, dict) else None
+            pixels = batch["image"] if isinstance(batch, dict) else batch
+            with torch.no_grad():
+                per_batch.append(self._embed(pixels.to(torch.float).to(self.device), supervised))
+            flags.append(flag)
+        return per_batch, flags
 
     def _embed(self, images, supervised, detach=True, provide_patch_shapes=False):
         """patchcore.py:355-431: returns the [B*P, D] embedding (as a list of numpy rows when
