@@ -106,3 +106,28 @@ def test_cli_synthetic_run(tmp_path):
     assert len(rows) == 2 and all(0.0 <= r[2] <= 1.0 for r in rows)
     p = tmp_path / "synthetic" / "wideresnet50" / "unsupervised" / "layer2_layer3_1024_1024_2.0_1.0" / "matrix_alpha_X_bottle_unsupervised.pickle"
     assert os.path.exists(p)
+
+
+def test_embed_over_dataloader_reference_convention():
+    """AnomalyClusteringCore.embed(DataLoader, supervised) -> (list of per-batch row lists, list of is_anomaly)
+    exactly as examples/main.py:266-267 consumes it: torch.tensor(Z) -> [N, P, D]."""
+    dev = torch.device("cuda")
+    net = backbones.load("dino_vitsmall8")
+    core = patchcore.AnomalyClusteringCore(dev).load(net, ["blocks.10", "blocks.11"], dev, (3, 224, 224), 256, 512, patchsize=3)
+    imgs = _images(3, seed=5)
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 3
+
+        def __getitem__(self, i):
+            return {"image": imgs[i], "is_anomaly": i % 2}
+
+    loader = torch.utils.data.DataLoader(DS(), batch_size=1, shuffle=False)
+    Z, labels = core.embed(loader, "unsupervised")
+    assert len(Z) == 3 and len(Z[0]) == 784 and [int(l) for l in labels] == [0, 1, 0]
+    Zt = torch.tensor(np.array(Z))
+    assert Zt.shape == (3, 784, 512)
+    direct = core.embed(imgs[1:2], "unsupervised")            # non-loader input goes straight to _embed
+    assert np.abs(np.stack(direct) - Zt[1].numpy()).max() <= 5e-5
+    assert patchcore.PatchMaker(3, 1).score(torch.tensor([[1.0, 5.0], [3.0, 2.0]])).tolist() == [5.0, 3.0]
