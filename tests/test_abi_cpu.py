@@ -93,3 +93,26 @@ def test_argument_validation_needs_no_gpu(lib_path):
         assert rc in (_lib.AC_ERR_CUDA, _lib.AC_ERR_DEVICE)
         with pytest.raises(_lib.AcError):
             _lib.check(rc, "ac_pairwise_l2")
+
+
+def test_plain_c_program_links_the_abi(lib_path, tmp_path):
+    """tests/c/abi_smoke.c compiles against include/ac_b200.h and links libac_b200.so with gcc (no Python,
+    no torch); without a B200 it must exit with the 'no device' code instead of computing anything."""
+    import shutil
+    import subprocess
+
+    import torch
+
+    gcc = shutil.which("gcc")
+    if gcc is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("no C toolchain / CUDA headers")
+    pkg = os.path.dirname(lib_path)
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run([gcc, os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-I" + os.path.join(ROOT, "include"),
+                    "-I/usr/local/cuda/include", "-L" + pkg, "-lac_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-lm",
+                    "-Wl,-rpath," + pkg, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout
+    else:
+        assert r.returncode == 2 and "no sm_100 device" in r.stdout

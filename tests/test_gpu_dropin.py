@@ -131,3 +131,25 @@ def test_embed_over_dataloader_reference_convention():
     direct = core.embed(imgs[1:2], "unsupervised")            # non-loader input goes straight to _embed
     assert np.abs(np.stack(direct) - Zt[1].numpy()).max() <= 5e-5
     assert patchcore.PatchMaker(3, 1).score(torch.tensor([[1.0, 5.0], [3.0, 2.0]])).tolist() == [5.0, 3.0]
+
+
+def test_plain_c_consumer_of_the_abi(tmp_path):
+    """tests/c/abi_smoke.c: a C program (no Python, no torch) links libac_b200.so through include/ac_b200.h."""
+    import os
+    import shutil
+    import subprocess
+
+    from anomaly_clustering_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("no C toolchain / CUDA headers on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run([gcc, os.path.join(root, "tests", "c", "abi_smoke.c"), "-I" + os.path.join(root, "include"),
+                    "-I/usr/local/cuda/include", "-L" + pkg, "-lac_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-lm",
+                    "-Wl,-rpath," + pkg, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max abs error" in r.stdout
