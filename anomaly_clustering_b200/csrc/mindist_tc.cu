@@ -59,6 +59,8 @@ struct __align__(64) TcParams {
   const int2* units;         // sym mode: explicit (query block, bank image) list in raster order (device-built)
   const long long* n_units;  // sym mode: length of that list (device memory)
   int win_begin, win_count;  // sym mode: only bank images in the circular window [win_begin, win_begin + win_count)
+  int dynamic;               // 1: units are claimed from a global counter (work stealing) instead of round-robin
+  unsigned long long* counter;
 };
 
 // Ownership of the unordered pair {i, j} of N images: the image that sees the other one within the
@@ -110,6 +112,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
       __trap();
     }
   }
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > kWatchdogCycles) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void st_cluster_s64(uint32_t cluster_addr, long long v) {
+  asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(cluster_addr), "l"(v) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -295,7 +322,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
   uint64_t* empty_bar = s_bar + kStages;      // [kStages]
   uint64_t* tfull_bar = s_bar + 2 * kStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  constexpr int kQD = 4;                                   // depth of the dynamic-scheduler unit queue
+  uint64_t* qfull_bar = tempty_bar + 2;                    // [kQD]
+  uint64_t* qempty_bar = qfull_bar + kQD;                  // [kQD] (the leader CTA's copy collects both CTAs' readers)
+  long long* s_qunit = reinterpret_cast<long long*>(qempty_bar + kQD);   // [kQD]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_qunit + kQD);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (G == 2) ? cluster_ctarank() : 0u;
@@ -313,6 +344,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
       mbar_init(smem_u32(&tfull_bar[b]), 1);
       mbar_init(smem_u32(&tempty_bar[b]), 4 * G);  // one arrival per epilogue warp of every CTA in the group
     }
+    for (int i = 0; i < kQD; ++i) {
+      mbar_init(smem_u32(&qfull_bar[i]), 1);
+      mbar_init(smem_u32(&qempty_bar[i]), 5 * G);  // readers: MMA warp (or the peer's producer) + 4 epilogue warps per CTA
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -324,13 +359,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
+  // ---- unit sequence.  static: u = worker, worker + nworkers, ...   dynamic: the leader's producer claims units
+  // from a global counter and publishes them through a kQD-deep smem queue to every other role of the group.
+  const uint32_t qempty_leader0 = (G == 2) ? mapa_rank(smem_u32(&qempty_bar[0]), 0) : smem_u32(&qempty_bar[0]);
+  auto queue_read = [&](uint32_t& qs, uint32_t& qph) -> long long {   // one lane per reader warp
+    mbar_wait_cluster(smem_u32(&qfull_bar[qs]), qph, p.err, 5);
+    const long long u = *reinterpret_cast<volatile long long*>(&s_qunit[qs]);
+    if (G == 2) mbar_arrive_cluster(qempty_leader0 + qs * 8);
+    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(qempty_leader0 + qs * 8) : "memory");
+    if (++qs == kQD) { qs = 0; qph ^= 1; }
+    return u;
+  };
+
   if (warp == 0) {
     // ================================================================ TMA producer
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       const uint64_t pol = l2_policy_evict_last();
       const uint32_t full0 = (G == 2) ? mapa_rank(smem_u32(&full_bar[0]), 0) : smem_u32(&full_bar[0]);
-      for (long long u = worker; u < total_units; u += nworkers) {
+      uint32_t qs = 0, qph = 0;
+      long long u_static = worker;
+      for (;;) {
+        long long u;
+        if (!p.dynamic) {
+          u = (u_static < total_units) ? u_static : -1;
+          u_static += nworkers;
+        } else if (leader) {
+          mbar_wait_cluster(smem_u32(&qempty_bar[qs]), qph ^ 1, p.err, 6);   // slot free in both CTAs
+          const unsigned long long c = atomicAdd(p.counter, 1ull);
+          u = (c < (unsigned long long)total_units) ? (long long)c : -1;
+          s_qunit[qs] = u;
+          asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&qfull_bar[qs])) : "memory");
+          if (G == 2) {
+            st_cluster_s64(mapa_rank(smem_u32(&s_qunit[qs]), 1), u);
+            mbar_arrive_cluster(mapa_rank(smem_u32(&qfull_bar[qs]), 1));
+          }
+          if (++qs == kQD) { qs = 0; qph ^= 1; }
+        } else {
+          u = queue_read(qs, qph);
+        }
+        if (u < 0) break;
         int mb, img;
         if (!decode_unit<G>(p, u, mb, img)) continue;
         const int arow = mb * (kTileM * G) + (int)rank * kTileM;
@@ -365,7 +433,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
     if (leader && elect_one()) {
       uint32_t stage = 0, phase = 0;
       uint32_t tile_ctr = 0;
-      for (long long u = worker; u < total_units; u += nworkers) {
+      uint32_t qs = 0, qph = 0;
+      long long u_static = worker;
+      for (;;) {
+        long long u;
+        if (!p.dynamic) {
+          u = (u_static < total_units) ? u_static : -1;
+          u_static += nworkers;
+        } else {
+          u = queue_read(qs, qph);
+        }
+        if (u < 0) break;
         int mb_, img_;
         if (!decode_unit<G>(p, u, mb_, img_)) continue;
         for (int t = 0; t < p.nt; ++t, ++tile_ctr) {
@@ -400,7 +478,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
     const int eidx = threadIdx.x - 64;            // 0..127
     const uint32_t tempty0 = (G == 2) ? mapa_rank(smem_u32(&tempty_bar[0]), 0) : smem_u32(&tempty_bar[0]);
     uint32_t tile_ctr = 0;
-    for (long long u = worker; u < total_units; u += nworkers) {
+    uint32_t qs = 0, qph = 0;
+    long long u_static = worker;
+    for (;;) {
+      long long u;
+      if (!p.dynamic) {
+        u = (u_static < total_units) ? u_static : -1;
+        u_static += nworkers;
+      } else {
+        long long uu = 0;
+        if (lane == 0) uu = queue_read(qs, qph);
+        else if (++qs == kQD) { qs = 0; qph ^= 1; }      // keep every lane's queue cursor in step
+        u = __shfl_sync(0xffffffffu, uu, 0);
+      }
+      if (u < 0) break;
       int mb, img;
       if (!decode_unit<G>(p, u, mb, img)) continue;
       const long long row = (long long)mb * (kTileM * G) + rank * kTileM + et;
@@ -522,7 +613,10 @@ __device__ __forceinline__ bool unit_has_work(const TcParams& p, int G, int mb, 
 __global__ void __launch_bounds__(1024) build_units_kernel(TcParams p, int G, int2* units, long long* n_units, int* err_flag) {
   __shared__ long long s_scan[1024];
   const int tid = threadIdx.x;
-  if (tid == 0 && err_flag) *err_flag = 0;
+  if (tid == 0 && err_flag) {
+    *err_flag = 0;
+    *reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(err_flag) + 128) = 0ull;   // dynamic-scheduler counter
+  }
   const int n_groups = (p.n_mblocks + p.GM - 1) / p.GM;
   const long long rows = (long long)n_groups * p.KU;
   const long long rows_per_mb = (long long)kTileM * G;
@@ -608,6 +702,7 @@ static uint32_t make_idesc(int M, int N, bool bf16) {
 }
 
 static int g_tc_cta_group = 2;   // test hook (ac_debug_set): 1 = single-CTA MMAs, 2 = CTA pairs
+static int g_tc_dynamic = 0;  // debug knob 4: dynamic unit scheduler (work stealing)
 static int g_tc_l2hint = 0;  // debug knob 3: L2 evict_last policy on operand loads (measured: no gain, off)
 static int g_tc_gm = 16;  // query blocks per raster group: 16 x 2 MB of A + the streaming bank images stay L2-resident (tuned on B200)
 
@@ -615,7 +710,7 @@ template <int G, int kStages>
 static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {
   constexpr int kBRows = kMaxN / G;
   constexpr size_t kStageBytes = (size_t)kTileM * kBlockK * 2 + (size_t)kBRows * kBlockK * 2;
-  const size_t smem = 1024 + kStages * kStageBytes + 2 * kMaxN * sizeof(float) + (2 * kStages + 4) * 8 + 16;
+  const size_t smem = 1024 + kStages * kStageBytes + 2 * kMaxN * sizeof(float) + (2 * kStages + 4) * 8 + 256;
   auto kern = mindist_tc_kernel<G, kStages>;
   AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long max_workers = (G == 2) ? num_sms / 2 : num_sms;
@@ -661,6 +756,8 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.n_mblocks = (int)ceil_div64(Mq, (long long)kTileM * G);
   prm.GM = g_tc_gm;
   prm.l2_hint = g_tc_l2hint;
+  prm.dynamic = g_tc_dynamic;
+  prm.counter = (unsigned long long*)((char*)err_flag + 128);   // inside the zeroed 256-byte workspace header
   prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin; prm.units = nullptr;
   prm.win_begin = win_begin; prm.win_count = (win_count < 0) ? nb_img : win_count;
   // bank images a raster group of GM query blocks can own: N/2 after each of the images it spans
@@ -714,6 +811,7 @@ extern "C" int ac_debug_set(int key, int value) {
   if (key == 0 && (value == 1 || value == 2)) { g_tc_cta_group = value; return AC_OK; }
   if (key == 1 && value >= 1) { g_tc_gm = value; return AC_OK; }
   if (key == 3 && (value == 0 || value == 1)) { g_tc_l2hint = value; return AC_OK; }
+  if (key == 4 && (value == 0 || value == 1)) { g_tc_dynamic = value; return AC_OK; }
   return AC_ERR_INVALID;
 }
 

@@ -62,3 +62,12 @@ for v in (4, 8, 12, 16, 24, 32):
     ms = run_sym(12)
     print("SYM GM=%d  %.2f ms  %.0f TFLOP/s executed, %.0f algorithmic" % (v, ms, 0.5 * flops / ms / 1e9, flops / ms / 1e9), flush=True)
 lib.ac_debug_set(1, 16)
+
+for dyn in (0, 1):
+    lib.ac_debug_set(4, dyn)
+    run_sym(2)
+    ms = run_sym(12)
+    run(2)
+    ms2 = run(6)
+    print("dynamic=%d  SYM %.2f ms   all-pairs %.2f ms" % (dyn, ms, ms2), flush=True)
+lib.ac_debug_set(4, 0)
