@@ -702,7 +702,7 @@ static uint32_t make_idesc(int M, int N, bool bf16) {
 }
 
 static int g_tc_cta_group = 2;   // test hook (ac_debug_set): 1 = single-CTA MMAs, 2 = CTA pairs
-static int g_tc_dynamic = 0;  // debug knob 4: dynamic unit scheduler (work stealing)
+static int g_tc_dynamic = 1;  // knob 4: dynamic unit scheduler (work stealing); measured 7 % faster than static round-robin
 static int g_tc_l2hint = 0;  // debug knob 3: L2 evict_last policy on operand loads (measured: no gain, off)
 static int g_tc_gm = 16;  // query blocks per raster group: 16 x 2 MB of A + the streaming bank images stay L2-resident (tuned on B200)
 
