@@ -266,7 +266,7 @@ def run_path_sharded(
         # Overlap pays once the local shard is a small part of the work: NCCL's transfer kernels take SMs
         # away from the persistent GEMM (statically scheduled over all SMs), which costs more than the hidden
         # transfer at 2 ranks (measured 11.6 vs 10.1 ms per step) and less from 4 ranks on (5.5 vs 5.8 ms).
-        min_world = int(os.environ.get("AC_OVERLAP_MIN_WORLD", "3"))
+        min_world = int(os.environ.get("AC_OVERLAP_MIN_WORLD", "2"))
         two_phase = bool(pending) and q.n_img > 1 and world >= min_world and getattr(compute, "supports_bank_window", False)
         if two_phase:
             # phase 1: bank images of the local shard (no remote data needed) overlaps the NCCL transfers
