@@ -263,9 +263,8 @@ def run_path_sharded(
     if use_sym:
         # every unordered image pair is multiplied once, by the rank that owns the pair's first image;
         # the column minima it produces for other ranks' query rows travel in one small all-to-all
-        # Overlap pays once the local shard is a small part of the work: NCCL's transfer kernels take SMs
-        # away from the persistent GEMM (statically scheduled over all SMs), which costs more than the hidden
-        # transfer at 2 ranks (measured 11.6 vs 10.1 ms per step) and less from 4 ranks on (5.5 vs 5.8 ms).
+        # NCCL's transfer kernels take a few SMs away from the persistent GEMM; its dynamic unit scheduler
+        # absorbs that (with the earlier static round-robin the overlap cost more than it hid at 2 ranks).
         min_world = int(os.environ.get("AC_OVERLAP_MIN_WORLD", "2"))
         two_phase = bool(pending) and q.n_img > 1 and world >= min_world and getattr(compute, "supports_bank_window", False)
         if two_phase:
