@@ -6,18 +6,23 @@
 //   dmin[j, r] = sqrt(max(0, |q_r|^2 + min_{c in image j} (|b_c|^2 - 2 q_r . b_c)))
 //
 // Structure (one persistent CTA -- or CTA pair with cta_group::2 -- per SM):
-//   warp 0      TMA producer: 128B-swizzled K-major operand tiles -> kStages-deep smem ring
+//   warp 0      TMA producer: 128B-swizzled K-major operand tiles -> kStages-deep smem ring; in the leader CTA it
+//               also CLAIMS the work units (global atomic counter) and publishes them to the other roles through
+//               a small smem queue (dynamic scheduling; the peer CTA's copy is written with st.shared::cluster)
 //   warp 1      MMA issuer:   tcgen05.mma kind::f16, fp32 accumulators in TMEM (2 x 256 columns,
 //               double buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
 //   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns, d2 = bn2[c] - 2*acc, running row-min in
 //               registers across the tiles of one bank image (each thread owns one query row, so
-//               the row-min needs no shuffles), sqrt + one coalesced store per (row, bank image).
+//               the row-min needs no shuffles), one coalesced store per (row, bank image).
 //   The [Mq, Nb*P] distance matrix never exists in memory.
 // Work unit = (block of 128*kCtaGroup query rows, bank image).  A bank image is cut into nt tiles
 // of <= 256 rows whose widths are multiples of 16 (P=784 -> 208+208+208+160), so no tile straddles
 // two images; excess columns of the last tile are masked with +inf norms.
 // Units are rasterised so that concurrently resident units share A blocks and bank images in L2.
 // The X3 precision modes run 3 K-segments (hi*hi, lo*hi, hi*lo) into the same accumulator.
+// Symmetric mode (ac_min_dist_sym): only the units of image pairs the query image OWNS are enumerated (device-built
+// raster list); the epilogue additionally reduces every column over the 32 rows of its warp (butterfly
+// transpose-min) and atomicMin's the result, so cdist(Zi,Zj) and cdist(Zj,Zi) come from one tile.
 #include "common.cuh"
 #include <cuda.h>
 #include <algorithm>
