@@ -6,6 +6,7 @@ extra keyword `precision` selects the tensor-core operand mode (default: module-
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -14,17 +15,20 @@ from .. import ops, pipeline
 
 PRECISION = "auto"  # auto | f16 | bf16 | f16x3 | bf16x3 | f32; auto = f16, or f16x3 for 0 < tau < 0.5
 
-_cache: Dict[Tuple, pipeline.PatchSet] = {}
+_cache: Dict[str, tuple] = {}
 
 
 def _patchset(Z: torch.Tensor, precision: str) -> pipeline.PatchSet:
-    """The reference API is stateless per call; operands of an unchanged Z are reused."""
-    key = (Z.data_ptr(), tuple(Z.shape), Z._version, precision, str(Z.device))
-    ps = _cache.get(key)
-    if ps is None:
-        _cache.clear()
-        ps = pipeline.patchset_from_Z(Z, precision)
-        _cache[key] = ps
+    """The reference API is stateless per call (Weight_Distance_*(Z, i, ...) is invoked once per image); the
+    operands of an UNCHANGED Z are reused.  The entry is tied to the tensor object itself (weak reference) and its
+    in-place version counter, so a different tensor that happens to reuse the same memory never hits."""
+    ent = _cache.get("z")
+    if ent is not None:
+        ref, version, prec, ps = ent
+        if ref() is Z and version == Z._version and prec == precision:
+            return ps
+    ps = pipeline.patchset_from_Z(Z, precision)
+    _cache["z"] = (weakref.ref(Z), Z._version, precision, ps)
     return ps
 
 
