@@ -221,6 +221,9 @@ def run_path_sharded(
         compute = _Cuda
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if n_total < world:
+        # an empty shard has no patch grid to agree on; callers with fewer images than ranks pass a sub-group
+        raise ValueError("run_path_sharded: %d images over %d ranks leaves empty shards; use a smaller group" % (n_total, world))
     bounds = shard_bounds(n_total, world)
     lo_i, hi_i = bounds[rank]
     z_free = (not keep_z) and hasattr(compute, "weighted_embed_from_features") and pipeline.z_free_supported(

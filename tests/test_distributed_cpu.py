@@ -76,19 +76,27 @@ class _OracleCompute:
             w[i] = dm[i][:, keep].mean(dim=1)
         return w
 
+    supports_bank_window = True      # exercises the two-phase (local shard first, remote shards after) schedule
+
     @staticmethod
-    def min_dist_sym(Qhi, Qlo, Qn2, q_img0, Bhi, Blo, Bn2, nb_img, P, precision):
-        """What ac_min_dist_sym produces: squared minima only for the pairs the query image owns."""
+    def min_dist_sym(Qhi, Qlo, Qn2, q_img0, Bhi, Blo, Bn2, nb_img, P, precision, bank_window=None, init=True, out=None):
+        """What ac_min_dist_sym produces: squared minima only for the pairs the query image owns, restricted
+        to the circular bank-image window; rows of Bhi outside the window are NOT read (they may still be
+        in flight), which the NaN poisoning below enforces."""
         nq = Qhi.shape[0] // P
-        d2 = torch.cdist(Qhi.double(), Bhi.double()).pow(2).float().reshape(nq, P, nb_img, P)
-        rowmin = torch.full((nb_img, nq * P), float("nan"))
-        colmin = torch.full((nq, nb_img * P), 3.0e38)
-        for il in range(nq):
-            for j in range(nb_img):
+        begin, count = bank_window if bank_window is not None else (0, nb_img)
+        window = [(begin + t) % nb_img for t in range(count)]
+        if init:
+            rowmin = torch.full((nb_img, nq * P), float("nan"))
+            colmin = torch.full((nq, nb_img * P), 3.0e38)
+        else:
+            rowmin, colmin = out
+        for j in window:
+            d2 = torch.cdist(Qhi.double(), Bhi[j * P:(j + 1) * P].double()).pow(2).float().reshape(nq, P, P)
+            for il in range(nq):
                 if distributed.pair_owned(q_img0 + il, j, nb_img):
-                    blk = d2[il, :, j, :]
-                    rowmin[j, il * P:(il + 1) * P] = blk.min(dim=1)[0]
-                    colmin[il, j * P:(j + 1) * P] = blk.min(dim=0)[0]
+                    rowmin[j, il * P:(il + 1) * P] = d2[il].min(dim=1)[0]
+                    colmin[il, j * P:(j + 1) * P] = torch.minimum(colmin[il, j * P:(j + 1) * P], d2[il].min(dim=0)[0])
         return rowmin, colmin
 
     @staticmethod
@@ -126,6 +134,11 @@ def _worker(rank, world, port, n_total, tmp):
 
     feats, _ = synth.planted_features(n_total, [(12, 6, 6, True), (12, 6, 6, True)], seed=3)
     lo, hi = distributed.shard_bounds(n_total, world)[rank]
+    if n_total < world:     # empty shards are refused on every rank, before any collective
+        with pytest.raises(ValueError, match="empty shards"):
+            distributed.run_path_sharded([f[lo:hi] for f in feats], n_total, 3, 1, 32, 64, [1.0], precision="f16", compute=_OracleCompute)
+        dist.destroy_process_group()
+        return
     # uneven all-gather of row blocks
     local = torch.arange(lo, hi, dtype=torch.float32).reshape(-1, 1).repeat(1, 3)
     allr = distributed.all_gather_rows(local, [b - a for a, b in distributed.shard_bounds(n_total, world)])
@@ -139,19 +152,24 @@ def _worker(rank, world, port, n_total, tmp):
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(300)
-def test_sharded_path_matches_single_process(tmp_path):
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("n_total,world,two_phase", [(5, 2, True), (5, 2, False), (7, 3, True), (3, 4, True)])
+def test_sharded_path_matches_single_process(tmp_path, monkeypatch, n_total, world, two_phase):
+    """Uneven shards (3+2, 3+2+2; 1+1+1+0 has an EMPTY rank and must be refused); with and without the two-phase schedule that
+    multiplies the local shard's pairs while the remote shards are still in flight."""
     from oracle import restated
 
     from anomaly_clustering_b200 import synth
 
-    n_total, world = 5, 2   # uneven split: 3 + 2
-    port = 29500 + (os.getpid() % 2000)
+    monkeypatch.setenv("AC_OVERLAP_MIN_WORLD", "2" if two_phase else "99")
+    port = 29500 + (os.getpid() * 7 + n_total * 13 + world * 101 + int(two_phase)) % 2000
     mp.spawn(_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
     feats, _ = synth.planted_features(n_total, [(12, 6, 6, True), (12, 6, 6, True)], seed=3)
     Z = restated.embed(feats, 3, 1, 32, 64).reshape(n_total, -1, 64)
     w = restated.weight_distance_unsupervised(Z)
     bounds = distributed.shard_bounds(n_total, world)
+    if n_total < world:
+        return
     for r in range(world):
         g = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
         lo, hi = bounds[r]
