@@ -63,3 +63,50 @@ def size_weighted_mean(values: Sequence[float], sizes: Sequence[int]) -> float:
     """test.py:286-325 -- object / texture aggregate rows of the tau-result CSV."""
     v, s = np.asarray(values, dtype=np.float64), np.asarray(sizes, dtype=np.float64)
     return float((v * s).sum() / s.sum())
+
+
+def evaluate_runs(outputs_root: str, dataset: str, backbone: str, supervised: str, layers: Sequence[str], pretrain_dim: int,
+                  target_dim: int, taus: Sequence[float], train_ratio: float = 1, objects: Sequence[str] = None,
+                  textures: Sequence[str] = None, dmat_fn=None, write_csv: bool = True):
+    """The `__main__` loop of test.py:228-325: for every tau and category load the (alpha, X) pickle and
+    info_<category>.pickle, cluster, and write <layers>_<Dp>_<D>_tau_result.csv with the size-weighted
+    'MVTec(object)' / 'MVTec(texture)' rows.  `dmat_fn(X ndarray) -> [N,N]` defaults to the library's
+    ac_pairwise_l2 on the GPU (stage a13); categories whose pickle is missing are skipped (the reference would
+    crash).  Returns the blocks written."""
+    import os
+
+    from . import io
+
+    if dmat_fn is None:
+        import torch
+
+        from . import ops
+
+        def dmat_fn(X):
+            return ops.pairwise_l2(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()).cpu().numpy()
+
+    objects = io.OBJECT if objects is None else list(objects)
+    textures = io.TEXTURE if textures is None else list(textures)
+    mode_dir = os.path.join(outputs_root, dataset, backbone, supervised)
+    blocks = []
+    for tau in taus:
+        rows, aggregates = [], []
+        for group, title in ((objects, "MVTec(object)"), (textures, "MVTec(texture)")):
+            vals, sizes = [], []
+            for category in group:
+                p = os.path.join(io.run_dir(mode_dir, layers, pretrain_dim, target_dim, tau, train_ratio),
+                                 "matrix_alpha_X_" + category + "_" + supervised + ".pickle")
+                ip = io.info_path(outputs_root, dataset, category)
+                if not (os.path.exists(p) and os.path.exists(ip)):
+                    continue
+                _, X = io.load_matrix_alpha_X(p)
+                nmi, ari, f1, label, _ = calculate_metrics(dmat_fn(X), io.anomaly_names(io.load_info(ip)))
+                rows.append((category, nmi, ari, f1))
+                vals.append((nmi, ari, f1))
+                sizes.append(len(label))
+            if vals:    # test.py:303-325: both aggregate rows follow all category rows
+                aggregates.append((title,) + tuple(size_weighted_mean([v[k] for v in vals], sizes) for k in range(3)))
+        blocks.append((tau, rows + aggregates))
+    if write_csv:
+        io.write_result_csv(io.result_csv_path(mode_dir, layers, pretrain_dim, target_dim), supervised, blocks)
+    return blocks

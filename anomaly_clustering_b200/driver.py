@@ -24,6 +24,11 @@ def _images(loader: Iterable) -> torch.Tensor:
     return torch.cat(ims, dim=0)
 
 
+def collect_info(loader: Iterable) -> list:
+    """main.py:253-262: every loader item minus its 'image' and 'mask' entries."""
+    return [{k: v for k, v in item.items() if k not in ("image", "mask")} for item in loader if isinstance(item, dict)]
+
+
 def make_category_data(
     path,
     category,
@@ -45,9 +50,14 @@ def make_category_data(
     precision: str = "auto",
     batch_size: int = 16,
     input_shape=(3, 224, 224),
+    info_root: Optional[str] = None,
+    keep_weights: bool = False,
 ):
     """Returns (matrix_alpha [N,1,P] f32 device tensor, X [N,D] f32 ndarray) for a scalar tau, a list of
-    such tuples for a list of taus, and writes the reference's pickle(s) when `save_path` is given."""
+    such tuples for a list of taus, and writes the reference's pickle(s) when `save_path` is given.
+    `info_root` (the reference's `outputs` directory) also writes <info_root>/<dataset>/info/info_<category>.pickle
+    from the loader's non-image fields (main.py:253-262, the file test.py:156 reads); `keep_weights` stores the
+    tau-independent weights next to the pickles so a later tau sweep can skip the distance pass."""
     if test_dataloader is None:
         raise ValueError("inject test_dataloader: the MVTec walker (datasets/mvtec.py) is out of scope and `path` is not read")
     device = device or torch.device("cuda", torch.cuda.current_device())
@@ -76,6 +86,8 @@ def make_category_data(
         return pipeline.PatchSet(sum(s.n_img for s in sets), first.P, first.D, first.grid, cat([s.Z for s in sets]),
                                  cat([s.hi for s in sets]), cat([s.lo for s in sets]), cat([s.n2 for s in sets]))
 
+    if info_root:
+        io.save_info(info_root, dataset, category, collect_info(test_dataloader))
     taus: List[float] = taus_early
     q = embed_all(test_dataloader, want_z=True)
     if supervised == "supervised":
@@ -93,6 +105,8 @@ def make_category_data(
     else:
         w = None                                      # main.py:290-291 'average'
     a64, a32, X, _ = pipeline.alpha_X_dist(q, w, taus)
+    if keep_weights and save_path and w is not None:
+        io.save_weights(save_path, category, supervised, w)
     results = []
     for t, tau_t in enumerate(taus if w is not None else taus[:1]):
         matrix_alpha = a32[t].unsqueeze(1)            # main.py:294

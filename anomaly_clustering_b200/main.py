@@ -16,7 +16,7 @@ import os
 
 import torch
 
-from . import backbones, cluster, driver
+from . import backbones, cluster, driver, io
 
 
 def synthetic_category(n_img: int, n_classes: int, seed: int, size: int = 224):
@@ -46,6 +46,17 @@ def synthetic_category(n_img: int, n_classes: int, seed: int, size: int = 224):
     return loader, labels
 
 
+def write_cli_csv(save_path, layers, pretrain_dim, target_dim, supervised, taus, rows) -> str:
+    """rows = [(category, tau, NMI, ARI, F1)] -> the reference's <layers>_<Dp>_<D>_tau_result.csv (test.py:246-325),
+    one block per tau, with the size-unweighted row set the CLI has (no object/texture split for synthetic data)."""
+    blocks = [(("%g" % t), [(c, n, a, f) for c, tt, n, a, f in rows if tt == t]) for t in taus]
+    return io.write_result_csv(io.result_csv_path(save_path, layers, pretrain_dim, target_dim), supervised, blocks)
+
+
+def _device() -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def main(argv=None):
     parser = argparse.ArgumentParser("Calculating Matrix (B200-native path)")
     parser.add_argument("--path", default="data/mvtec_ad", type=str, help="Path to the dataset (unused for --dataset synthetic).")
@@ -68,7 +79,7 @@ def main(argv=None):
     if args.dataset != "synthetic":
         raise SystemExit("only --dataset synthetic is available offline; for real data call "
                          "anomaly_clustering_b200.driver.make_category_data(..., test_dataloader=..., backbone=...)")
-    device = torch.device("cuda", torch.cuda.current_device())
+    device = _device()
     net = backbones.load(args.backbone_names[0])
     save_path = os.path.join(args.output_dir, args.dataset, args.backbone_names[0], args.supervised)
     os.makedirs(save_path, exist_ok=True)
@@ -82,7 +93,8 @@ def main(argv=None):
                                         args.backbone_names, args.layers_to_extract_from, args.patchsize, save_path,
                                         train_ratio=args.train_ratio, tau=list(args.tau), supervised=args.supervised,
                                         dataset=args.dataset, test_dataloader=loader, train_dataloader=train, backbone=net,
-                                        device=device, precision=args.precision)
+                                        device=device, precision=args.precision,
+                                        info_root=args.output_dir)
         from . import ops
 
         for (alpha, X), tau in zip(res, args.tau):
@@ -90,6 +102,8 @@ def main(argv=None):
             nmi, ari, f1, _, _ = cluster.calculate_metrics(Dm, labels)
             print("%s  tau=%g\nNMI: %s\nARI: %s\nF1:%s\n" % (category, tau, nmi, ari, f1))
             rows.append((category, tau, nmi, ari, f1))
+    write_cli_csv(save_path, args.layers_to_extract_from, args.pretrain_embed_dimension, args.target_embed_dimension,
+                  args.supervised, list(args.tau), rows)
     return rows
 
 
