@@ -142,6 +142,19 @@ def start_all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None
     buf[start:start + counts[rank]].copy_(local)
     if all(c == counts[0] for c in counts):
         work = dist.all_gather_into_tensor(buf, local, group=group, async_op=True)
+    elif dist.get_backend(group) != "nccl":
+        # gloo (CPU tests) rejects all_gather on unequal blocks: point-to-point exchange of the same blocks
+        world = dist.get_world_size(group)
+        offs = [sum(counts[:r]) for r in range(world)]
+        ops_ = []
+        for peer in range(world):
+            if peer == rank:
+                continue
+            if counts[rank] > 0:
+                ops_.append(dist.P2POp(dist.isend, local, peer, group=group))
+            if counts[peer] > 0:
+                ops_.append(dist.P2POp(dist.irecv, buf[offs[peer]:offs[peer] + counts[peer]], peer, group=group))
+        return buf, (dist.batch_isend_irecv(ops_) if ops_ else [])
     else:
         views, s0 = [], 0
         for c in counts:
@@ -307,3 +320,103 @@ def run_path_sharded(
     pipeline._mark("xgather_end")
     Dm = torch.stack([compute.pairwise_l2(X_all[t]) for t in range(len(taus))])
     return a64, X_all, Dm, w
+
+
+def run_path_sharded_supervised(
+    local_features: Sequence[torch.Tensor],
+    n_total: int,
+    local_bank_features: Sequence[torch.Tensor],
+    n_bank_total: int,
+    patchsize: int,
+    stride: int,
+    pretrain_dim: int,
+    target_dim: int,
+    taus: Sequence[float] = (1.0,),
+    precision: str = "auto",
+    group=None,
+    compute=None,
+    overlap: bool = True,
+):
+    """Supervised path (utils.py:230-237, 260-277) sharded both ways: the n_total query
+    images by shard_bounds(n_total), the n_bank_total normal images by shard_bounds(n_bank_total) for the embed
+    only; the bank's tensor-core operands (+ norms; fp32 Z for precision 'f32') are all-gathered and every rank
+    takes w = min over ALL bank images for its own queries.  The min over bank images splits over bank pieces, so
+    the local bank shard is multiplied while the gather is in flight (`overlap`), the remote pieces after it.
+    Returns (alpha64_local [T,n_r,P], X_all [T,N,D], Dmat [T,N,N], w_local) like run_path_sharded.
+    `compute`: tests only, see run_path_sharded."""
+    from . import pipeline
+
+    precision = pipeline.resolve_precision(precision, taus)
+    if compute is None:
+        from . import ops
+
+        class _Cuda:
+            embed_images = staticmethod(pipeline.embed_images)
+            min_distance_weights = staticmethod(pipeline.min_distance_weights)
+            alpha = staticmethod(ops.alpha)
+            weighted_embed = staticmethod(ops.weighted_embed)
+            pairwise_l2 = staticmethod(ops.pairwise_l2)
+
+        compute = _Cuda
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if n_total < world or n_bank_total < world:
+        raise ValueError("run_path_sharded_supervised: %d query / %d bank images over %d ranks leaves empty shards; "
+                         "use a smaller group" % (n_total, n_bank_total, world))
+    qb, bb = shard_bounds(n_total, world), shard_bounds(n_bank_total, world)
+    q = compute.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=True)
+    b_loc = compute.embed_images(local_bank_features, patchsize, stride, pretrain_dim, target_dim, precision,
+                                 want_z=(precision == "f32"))
+    assert q.n_img == qb[rank][1] - qb[rank][0] and b_loc.n_img == bb[rank][1] - bb[rank][0] and b_loc.P == q.P
+    P = q.P
+    counts = [(b - a) * P for a, b in bb]
+
+    def piece(bufs, a, b):
+        """Bank images [a, b) of the gathered buffers as a PatchSet (row slices of contiguous buffers)."""
+        Zb, hib, lob, n2b = bufs
+        cut = lambda t: None if t is None else t[a * P : b * P]  # noqa: E731
+        return pipeline.PatchSet(b - a, P, q.D, q.grid, Z=cut(Zb), hi=cut(hib), lo=cut(lob), n2=cut(n2b))
+
+    pipeline._mark("gather_begin")
+    pending = []
+    if precision == "f32":
+        Zb, r0 = start_all_gather_rows(b_loc.Z, counts, group)
+        bufs, pending = (Zb, None, None, None), list(r0)
+    else:
+        hib, r1 = start_all_gather_rows(b_loc.hi, counts, group)
+        lob, r2 = (None, []) if b_loc.lo is None else start_all_gather_rows(b_loc.lo, counts, group)
+        n2b, r3 = start_all_gather_rows(b_loc.n2, counts, group)
+        bufs, pending = (None, hib, lob, n2b), list(r1) + list(r2) + list(r3)
+    pipeline._mark("gather_end")
+    lo_b, hi_b = bb[rank]
+    w = None
+    if overlap and world > 1:
+        w = compute.min_distance_weights(q, piece(bufs, lo_b, hi_b), "supervised", precision)   # local shard: already valid
+        rest = [(0, lo_b), (hi_b, n_bank_total)]
+    else:
+        rest = [(0, n_bank_total)]
+    for r in pending:
+        r.wait()
+    for a, b in rest:
+        if b > a:
+            wp = compute.min_distance_weights(q, piece(bufs, a, b), "supervised", precision)
+            w = wp if w is None else torch.minimum(w, wp)
+    a64, a32 = compute.alpha(w, list(taus))
+    Z3 = q.Z.reshape(q.n_img, P, q.D)
+    X_loc = torch.stack([compute.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)      # [n_r, T, D]
+    pipeline._mark("xgather_begin")
+    X_all = all_gather_rows(X_loc, [b - a for a, b in qb], group).permute(1, 0, 2).contiguous()     # [T, N, D]
+    pipeline._mark("xgather_end")
+    Dm = torch.stack([compute.pairwise_l2(X_all[t]) for t in range(len(taus))])
+    return a64, X_all, Dm, w
+
+
+def run_categories_sharded(sizes: Sequence[int], run_category, group=None):
+    """Per-category banks (the reference's own semantics: one make_category_data per category, main.py:353):
+    whole categories are assigned to ranks by greedy LPT on n_c * (n_c - 1) (the pair count)
+    and each rank calls `run_category(c)` for its own; there is no collective on the data path.
+    Returns {category index: result} for this rank's categories and the full assignment."""
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    bins = lpt_assign([float(n) * (n - 1) for n in sizes], world)
+    return {c: run_category(c) for c in bins[rank]}, bins

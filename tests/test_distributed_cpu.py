@@ -71,6 +71,9 @@ class _OracleCompute:
         dm = restated.per_image_min_dist(q.Z.reshape(q.n_img, q.P, q.D), bank.hi.reshape(bank.n_img, bank.P, bank.D))
         w = torch.empty(q.n_img, q.P)
         for i in range(q.n_img):
+            if mode == "supervised":                    # utils.py:236: min over the bank images
+                w[i] = dm[i].min(dim=1)[0]
+                continue
             keep = torch.ones(bank.n_img, dtype=torch.bool)
             keep[int(q_self[i])] = False
             w[i] = dm[i][:, keep].mean(dim=1)
@@ -179,4 +182,54 @@ def test_sharded_path_matches_single_process(tmp_path, monkeypatch, n_total, wor
             assert np.abs(g["a"][ti] - a[lo:hi].numpy()).max() <= 1e-6
             X = restated.weighted_embedding(a, Z)
             assert np.abs(g["X"][ti] - X).max() <= 1e-5           # every rank holds ALL X rows, in global order
+            assert np.abs(g["D"][ti] - restated.pairwise_euclidean(X)).max() <= 1e-4
+
+
+def _worker_supervised(rank, world, port, n_total, n_bank, overlap, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from anomaly_clustering_b200 import synth
+
+    layers = [(12, 6, 6, True), (12, 6, 6, True)]
+    feats, _ = synth.planted_features(n_total, layers, seed=3)
+    bank, _ = synth.planted_features(n_bank, layers, seed=11)
+    (lo, hi), (blo, bhi) = distributed.shard_bounds(n_total, world)[rank], distributed.shard_bounds(n_bank, world)[rank]
+    a64, X, Dm, w = distributed.run_path_sharded_supervised([f[lo:hi] for f in feats], n_total, [f[blo:bhi] for f in bank], n_bank,
+                                                            3, 1, 32, 64, [1.0, 2.0], precision="f16", compute=_OracleCompute,
+                                                            overlap=overlap)
+    np.savez(os.path.join(tmp, "r%d.npz" % rank), a=a64.numpy(), X=X.numpy(), D=Dm.numpy(), w=w.numpy())
+    cats, bins = distributed.run_categories_sharded([83, 150, 132, 110, 115], lambda c: c * 10)
+    assert cats == {c: c * 10 for c in bins[rank]} and sorted(c for b in bins for c in b) == [0, 1, 2, 3, 4]
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("n_total,n_bank,world,overlap", [(5, 7, 2, True), (5, 7, 2, False), (4, 5, 3, True)])
+def test_supervised_sharded_matches_single_process(tmp_path, n_total, n_bank, world, overlap):
+    """Queries and the normal-image bank both sharded unevenly; w = min over ALL bank images whichever rank
+    embedded them, with the local bank shard multiplied before the gather completes."""
+    from oracle import restated
+
+    from anomaly_clustering_b200 import synth
+
+    port = 29500 + (os.getpid() * 5 + n_total * 17 + n_bank * 29 + world * 211 + int(overlap)) % 2000
+    mp.spawn(_worker_supervised, args=(world, port, n_total, n_bank, overlap, str(tmp_path)), nprocs=world, join=True)
+    layers = [(12, 6, 6, True), (12, 6, 6, True)]
+    feats, _ = synth.planted_features(n_total, layers, seed=3)
+    bank, _ = synth.planted_features(n_bank, layers, seed=11)
+    Z = restated.embed(feats, 3, 1, 32, 64).reshape(n_total, -1, 64)
+    Zb = restated.embed(bank, 3, 1, 32, 64).reshape(n_bank, -1, 64)
+    w = restated.weight_distance_supervised(Z, Zb)
+    bounds = distributed.shard_bounds(n_total, world)
+    for r in range(world):
+        g = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
+        lo, hi = bounds[r]
+        assert np.abs(g["w"] - w[lo:hi].numpy()).max() <= 1e-5
+        for ti, tau in enumerate([1.0, 2.0]):
+            a = restated.alpha_from_weights(w, tau)
+            assert np.abs(g["a"][ti] - a[lo:hi].numpy()).max() <= 1e-6
+            X = restated.weighted_embedding(a, Z)
+            assert np.abs(g["X"][ti] - X).max() <= 1e-5
             assert np.abs(g["D"][ti] - restated.pairwise_euclidean(X)).max() <= 1e-4
