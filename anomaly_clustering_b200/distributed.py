@@ -131,6 +131,44 @@ def start_gather_needed_rows(local: torch.Tensor, bounds: Sequence[Tuple[int, in
     return buf, reqs
 
 
+def start_shard_pipeline(locals_: Sequence[Optional[torch.Tensor]], bounds: Sequence[Tuple[int, int]], rows_per_item: int,
+                         need: Sequence[Sequence[int]], group=None):
+    """Needed-shard transfers as a ring of pairwise steps: step k (k = 1 .. world-1) receives the shard of rank
+    (rank + k) % world and sends the local shard to rank (rank - k) % world, when the receiver needs it -- both
+    sides evaluate the same predicate, so every step is a matched exchange.  Each step is its own batch, so the
+    caller can multiply against shard k while shards k+1.. are still in flight (they arrive in the order the
+    symmetric kernel's circular bank window consumes them).  `locals_` are row blocks that travel together
+    (operand hi / lo / norms; None entries are skipped).  Returns (buffers, [(source rank, requests), ...])."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    total = bounds[-1][1] * rows_per_item
+    a, b = bounds[rank]
+    bufs = []
+    for t in locals_:
+        if t is None:
+            bufs.append(None)
+            continue
+        buf = torch.empty((total,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        buf[a * rows_per_item : b * rows_per_item].copy_(t)
+        bufs.append(buf)
+    srcs = [t.contiguous() for t in locals_ if t is not None]
+    dsts = [x for x in bufs if x is not None]
+    steps = []
+    for k in range(1, world):
+        src, dst = (rank + k) % world, (rank - k) % world
+        ops_ = []
+        if rank in need[dst]:
+            ops_ += [dist.P2POp(dist.isend, t, dst, group=group) for t in srcs]
+        if src in need[rank]:
+            sa, sb = bounds[src]
+            ops_ += [dist.P2POp(dist.irecv, x[sa * rows_per_item : sb * rows_per_item], src, group=group) for x in dsts]
+        reqs = dist.batch_isend_irecv(ops_) if ops_ else []
+        if src in need[rank]:
+            steps.append((src, reqs))
+        elif reqs:
+            steps.append((None, reqs))       # send-only step: nothing to multiply, but the requests must complete
+    return bufs, steps
+
+
 def start_all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None):
     """Asynchronous all-gather of row blocks into one buffer whose local slice is already valid, so work on
     the local shard can overlap the collective.  Returns (buffer, [work])."""
@@ -248,7 +286,15 @@ def run_path_sharded(
     use_sym = symmetric and precision != "f32" and P >= 32 and hasattr(compute, "min_dist_sym")
     pipeline._mark("gather_begin")
     pending = []
-    if use_sym:
+    pipeline_steps = None
+    # opt-in (AC_SHARD_PIPELINE=1): shard-granular pipeline -- multiply against shard k while shards k+1.. travel
+    shard_pipeline = (use_sym and world > 2 and os.environ.get("AC_SHARD_PIPELINE", "0") == "1"
+                      and getattr(compute, "supports_bank_window", False))
+    if shard_pipeline:
+        (hi_buf, lo_buf, n2_buf), pipeline_steps = start_shard_pipeline([q.hi, q.lo, q.n2], bounds, P,
+                                                                        needed_shards(bounds, n_total), group)
+        bank = pipeline.PatchSet(n_total, P, q.D, q.grid, hi=hi_buf, lo=lo_buf, n2=n2_buf)
+    elif use_sym:
         # only the shards that hold bank images of pairs this rank owns (the next n_total//2 images);
         # the transfers stay in flight while the pairs inside the local shard are multiplied
         if 3 <= world <= 4 or dist.get_backend(group) != "nccl":
@@ -283,7 +329,23 @@ def run_path_sharded(
         # absorbs that (with the earlier static round-robin the overlap cost more than it hid at 2 ranks).
         min_world = int(os.environ.get("AC_OVERLAP_MIN_WORLD", "2"))
         two_phase = bool(pending) and q.n_img > 1 and world >= min_world and getattr(compute, "supports_bank_window", False)
-        if two_phase:
+        if shard_pipeline:
+            windows = [((lo_i, q.n_img), [])] if q.n_img > 1 else []          # the local shard needs no transfer
+            for src, reqs in pipeline_steps:
+                windows.append((None if src is None else (bounds[src][0], bounds[src][1] - bounds[src][0]), reqs))
+            out, first = None, True
+            for window, reqs in windows:
+                for r in reqs:
+                    r.wait()
+                if window is None:
+                    continue
+                pipeline._mark("mindist_begin")
+                out = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,
+                                           bank_window=window, init=first, out=out)
+                pipeline._mark("mindist_end")
+                first = False
+            rowmin, colmin = out
+        elif two_phase:
             # phase 1: bank images of the local shard (no remote data needed) overlaps the NCCL transfers
             pipeline._mark("mindist_begin")
             out = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,

@@ -20,8 +20,9 @@ for n_img, layers, Dp, D in ((13, [(96, 12, 12, True), (96, 12, 12, True)], 256,
     bounds = distributed.shard_bounds(n_img, world)
     lo, hi = bounds[rank]
     feats, _ = synth.planted_features_device(range(lo, hi), layers, device="cuda")
-    for sym in (True, False):
-        a64, X, Dm, w = distributed.run_path_sharded(feats, n_img, 3, 1, Dp, D, [1.0, 2.0], symmetric=sym)
+    for sym in (True, "pipeline", False):
+        os.environ["AC_SHARD_PIPELINE"] = "1" if sym == "pipeline" else "0"     # opt-in shard-granular schedule (world > 2)
+        a64, X, Dm, w = distributed.run_path_sharded(feats, n_img, 3, 1, Dp, D, [1.0, 2.0], symmetric=bool(sym))
         if rank == 0:
             allf, _ = synth.planted_features_device(range(n_img), layers, device="cuda")
             ref = pipeline.run_path(allf, 3, 1, Dp, D, "unsupervised", [1.0, 2.0])

@@ -80,6 +80,7 @@ class _OracleCompute:
         return w
 
     supports_bank_window = True      # exercises the two-phase (local shard first, remote shards after) schedule
+    windows = []                     # bank windows of the min_dist_sym calls, for the schedule assertions
 
     @staticmethod
     def min_dist_sym(Qhi, Qlo, Qn2, q_img0, Bhi, Blo, Bn2, nb_img, P, precision, bank_window=None, init=True, out=None):
@@ -88,6 +89,7 @@ class _OracleCompute:
         in flight), which the NaN poisoning below enforces."""
         nq = Qhi.shape[0] // P
         begin, count = bank_window if bank_window is not None else (0, nb_img)
+        _OracleCompute.windows.append((int(begin), int(count)))
         window = [(begin + t) % nb_img for t in range(count)]
         if init:
             rowmin = torch.full((nb_img, nq * P), float("nan"))
@@ -148,15 +150,18 @@ def _worker(rank, world, port, n_total, tmp):
     assert torch.equal(allr[:, 0], torch.arange(n_total, dtype=torch.float32))
     a64, X, Dm, w = distributed.run_path_sharded([f[lo:hi] for f in feats], n_total, 3, 1, 32, 64, [1.0, 2.0], precision="f16",
                                                  compute=_OracleCompute, symmetric=True)
+    windows = list(_OracleCompute.windows)
     _, _, _, w_full = distributed.run_path_sharded([f[lo:hi] for f in feats], n_total, 3, 1, 32, 64, [1.0], precision="f16",
                                                    compute=_OracleCompute, symmetric=False)
     assert (w - w_full).abs().max().item() <= 1e-4      # symmetric exchange == straightforward all-pairs
-    np.savez(os.path.join(tmp, "r%d.npz" % rank), a=a64.numpy(), X=X.numpy(), D=Dm.numpy(), w=w.numpy())
+    np.savez(os.path.join(tmp, "r%d.npz" % rank), a=a64.numpy(), X=X.numpy(), D=Dm.numpy(), w=w.numpy(),
+             windows=np.asarray(windows, dtype=np.int64).reshape(-1, 2))
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("n_total,world,two_phase", [(5, 2, True), (5, 2, False), (7, 3, True), (3, 4, True)])
+@pytest.mark.parametrize("n_total,world,two_phase", [(5, 2, True), (5, 2, False), (7, 3, True), (3, 4, True),
+                                                     (7, 3, "pipeline"), (9, 4, "pipeline"), (4, 4, "pipeline")])
 def test_sharded_path_matches_single_process(tmp_path, monkeypatch, n_total, world, two_phase):
     """Uneven shards (3+2, 3+2+2; 1+1+1+0 has an EMPTY rank and must be refused); with and without the two-phase schedule that
     multiplies the local shard's pairs while the remote shards are still in flight."""
@@ -165,7 +170,9 @@ def test_sharded_path_matches_single_process(tmp_path, monkeypatch, n_total, wor
     from anomaly_clustering_b200 import synth
 
     monkeypatch.setenv("AC_OVERLAP_MIN_WORLD", "2" if two_phase else "99")
-    port = 29500 + (os.getpid() * 7 + n_total * 13 + world * 101 + int(two_phase)) % 2000
+    # "pipeline": shard-granular schedule (one launch per arriving shard; 4 images on 4 ranks = no local pairs at all)
+    monkeypatch.setenv("AC_SHARD_PIPELINE", "1" if two_phase == "pipeline" else "0")
+    port = 29500 + (os.getpid() * 7 + n_total * 13 + world * 101 + len(str(two_phase))) % 2000
     mp.spawn(_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
     feats, _ = synth.planted_features(n_total, [(12, 6, 6, True), (12, 6, 6, True)], seed=3)
     Z = restated.embed(feats, 3, 1, 32, 64).reshape(n_total, -1, 64)
@@ -176,6 +183,15 @@ def test_sharded_path_matches_single_process(tmp_path, monkeypatch, n_total, wor
     for r in range(world):
         g = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
         lo, hi = bounds[r]
+        wins = [tuple(x) for x in g["windows"]]
+        if two_phase == "pipeline":      # local shard (when it has pairs), then one launch per needed shard in ring order
+            need = distributed.needed_shards(bounds, n_total)[r]
+            ring = [s for s in ((r + k) % world for k in range(1, world)) if s in need]
+            assert wins == ([(lo, hi - lo)] if hi - lo > 1 else []) + [(bounds[s][0], bounds[s][1] - bounds[s][0]) for s in ring]
+        elif two_phase and hi - lo > 1:
+            assert wins == [(lo, hi - lo), (hi % n_total, n_total - (hi - lo))]
+        else:
+            assert wins == [(0, n_total)]
         assert np.abs(g["w"] - w[lo:hi].numpy()).max() <= 1e-5
         for ti, tau in enumerate([1.0, 2.0]):
             a = restated.alpha_from_weights(w, tau)
