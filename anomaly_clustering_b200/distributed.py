@@ -153,20 +153,28 @@ def start_shard_pipeline(locals_: Sequence[Optional[torch.Tensor]], bounds: Sequ
     srcs = [t.contiguous() for t in locals_ if t is not None]
     dsts = [x for x in bufs if x is not None]
     steps = []
+    for send_to, recv_from in shard_pipeline_plan(need, rank, world):
+        ops_ = []
+        if send_to is not None:
+            ops_ += [dist.P2POp(dist.isend, t, send_to, group=group) for t in srcs]
+        if recv_from is not None:
+            sa, sb = bounds[recv_from]
+            ops_ += [dist.P2POp(dist.irecv, x[sa * rows_per_item : sb * rows_per_item], recv_from, group=group) for x in dsts]
+        reqs = dist.batch_isend_irecv(ops_) if ops_ else []
+        if recv_from is not None or reqs:
+            steps.append((recv_from, reqs))  # recv_from None = send-only step: nothing to multiply, requests must complete
+    return bufs, steps
+
+
+def shard_pipeline_plan(need: Sequence[Sequence[int]], rank: int, world: int) -> List[Tuple[Optional[int], Optional[int]]]:
+    """Pure host logic of start_shard_pipeline: for ring step k = 1 .. world-1 the pair (send_to, recv_from) of this
+    rank, None where nothing travels.  Rank r sends to d = r-k exactly when d receives from d+k = r, so the steps of all
+    ranks pair up one to one (tests/test_distributed_cpu.py simulates every rank and checks it)."""
+    plan = []
     for k in range(1, world):
         src, dst = (rank + k) % world, (rank - k) % world
-        ops_ = []
-        if rank in need[dst]:
-            ops_ += [dist.P2POp(dist.isend, t, dst, group=group) for t in srcs]
-        if src in need[rank]:
-            sa, sb = bounds[src]
-            ops_ += [dist.P2POp(dist.irecv, x[sa * rows_per_item : sb * rows_per_item], src, group=group) for x in dsts]
-        reqs = dist.batch_isend_irecv(ops_) if ops_ else []
-        if src in need[rank]:
-            steps.append((src, reqs))
-        elif reqs:
-            steps.append((None, reqs))       # send-only step: nothing to multiply, but the requests must complete
-    return bufs, steps
+        plan.append((dst if rank in need[dst] else None, src if src in need[rank] else None))
+    return plan
 
 
 def start_all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None):

@@ -41,6 +41,23 @@ def test_needed_shards_cover_owned_pairs_only():
             assert max(len(x) for x in need) <= 5      # about half of the 7 other ranks
 
 
+def test_shard_pipeline_steps_pair_up_on_every_rank():
+    """Simulates all ranks of the ring schedule: within each step every send has exactly one matching receive
+    on the destination (an unmatched NCCL send/recv would hang the job), and over all steps a rank receives
+    exactly its needed shards, in ring order."""
+    for n, world in ((100, 8), (1210, 8), (13, 3), (21, 4), (9, 4), (4, 4), (7, 5), (64, 8), (8, 8), (100, 7)):
+        bounds = distributed.shard_bounds(n, world)
+        need = distributed.needed_shards(bounds, n)
+        plans = [distributed.shard_pipeline_plan(need, r, world) for r in range(world)]
+        for k in range(world - 1):
+            sends = {(r, plans[r][k][0]) for r in range(world) if plans[r][k][0] is not None}
+            recvs = {(plans[r][k][1], r) for r in range(world) if plans[r][k][1] is not None}
+            assert sends == recvs, (n, world, k)
+        for r in range(world):
+            got = [p[1] for p in plans[r] if p[1] is not None]
+            assert sorted(got) == sorted(need[r]) and got == [s for s in ((r + k) % world for k in range(1, world)) if s in need[r]]
+
+
 def test_shard_bounds_and_lpt():
     assert distributed.shard_bounds(100, 8) == [(0, 13), (13, 26), (26, 39), (39, 52), (52, 64), (64, 76), (76, 88), (88, 100)]
     assert distributed.shard_bounds(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
