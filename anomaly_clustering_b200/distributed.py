@@ -299,8 +299,16 @@ def run_path_sharded(
     shard_pipeline = (use_sym and world > 2 and os.environ.get("AC_SHARD_PIPELINE", "0") == "1"
                       and getattr(compute, "supports_bank_window", False))
     if shard_pipeline:
-        (hi_buf, lo_buf, n2_buf), pipeline_steps = start_shard_pipeline([q.hi, q.lo, q.n2], bounds, P,
-                                                                        needed_shards(bounds, n_total), group)
+        need_all = needed_shards(bounds, n_total)
+        if os.environ.get("AC_SHARD_TRANSPORT", "nccl") == "symm" and dist.get_backend(group) == "nccl":
+            # copy-engine pulls from symmetric memory instead of NCCL send/recv kernels (symm_transport.py; not yet
+            # run on hardware -- opt-in only)
+            from .symm_transport import SymmetricBank
+
+            sb_ = SymmetricBank.get(n_total * P, q.D, q.hi.dtype, q.lo is not None, q.hi.device, group)
+            (hi_buf, lo_buf, n2_buf), pipeline_steps = sb_.start(q.hi, q.lo, q.n2, bounds, P, need_all[rank], rank, world)
+        else:
+            (hi_buf, lo_buf, n2_buf), pipeline_steps = start_shard_pipeline([q.hi, q.lo, q.n2], bounds, P, need_all, group)
         bank = pipeline.PatchSet(n_total, P, q.D, q.grid, hi=hi_buf, lo=lo_buf, n2=n2_buf)
     elif use_sym:
         # only the shards that hold bank images of pairs this rank owns (the next n_total//2 images);

@@ -20,8 +20,10 @@ for n_img, layers, Dp, D in ((13, [(96, 12, 12, True), (96, 12, 12, True)], 256,
     bounds = distributed.shard_bounds(n_img, world)
     lo, hi = bounds[rank]
     feats, _ = synth.planted_features_device(range(lo, hi), layers, device="cuda")
-    for sym in (True, "pipeline", False):
-        os.environ["AC_SHARD_PIPELINE"] = "1" if sym == "pipeline" else "0"     # opt-in shard-granular schedule (world > 2)
+    variants = (True, "pipeline", False) + (("pipeline-symm",) if os.environ.get("AC_CHECK_SYMM") == "1" else ())
+    for sym in variants:
+        os.environ["AC_SHARD_PIPELINE"] = "1" if str(sym).startswith("pipeline") else "0"   # opt-in shard-granular schedule (world > 2)
+        os.environ["AC_SHARD_TRANSPORT"] = "symm" if sym == "pipeline-symm" else "nccl"   # AC_CHECK_SYMM=1: copy-engine pulls
         a64, X, Dm, w = distributed.run_path_sharded(feats, n_img, 3, 1, Dp, D, [1.0, 2.0], symmetric=bool(sym))
         if rank == 0:
             allf, _ = synth.planted_features_device(range(n_img), layers, device="cuda")
