@@ -100,3 +100,37 @@ def test_oracle_against_live_reference():
     ar = ref_import.reference_alpha_unsupervised(1.0, Z)
     ao = restated.matrix_alpha_unsupervised(1.0, Z)
     assert (ar - ao).abs().max().item() <= 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Anomaly-Clustering"), reason="reference tree absent")
+def test_oracle_fuzz_against_live_reference():
+    """Build container only: 24 seeded random geometries (CNN pyramids with 1-3 layers of different grids, ViT
+    token layers, patch size 1/3/5, stride 1/2, pooling up and down, aggregator windows that straddle layers)
+    through the imported reference's _embed, and random-tau alpha in both modes, against the restatement."""
+    from oracle import ref_import
+
+    rng = np.random.default_rng(2023)
+    gen = torch.Generator().manual_seed(2023)
+    for case in range(24):
+        k = int(rng.choice([1, 3, 3, 3, 5]))
+        s = int(rng.choice([1, 1, 1, 2]))
+        B = int(rng.integers(1, 3))
+        if case % 3 == 0:      # ViT tokens: all layers share the grid
+            g = int(rng.integers(4, 9))
+            feats = [torch.randn(B, 1 + g * g, int(rng.integers(8, 40)), generator=gen) for _ in range(int(rng.integers(1, 4)))]
+        else:                  # CNN pyramid: grid halves per layer
+            g = int(rng.choice([8, 12, 16]))
+            L = int(rng.integers(1, 4))
+            feats = [torch.randn(B, int(rng.integers(6, 30)), max(g >> l, k), max(g >> l, k), generator=gen) for l in range(L)]
+        Dp, D = int(rng.integers(5, 70)), int(rng.integers(5, 90))
+        zr = ref_import.reference_embed(feats, k, s, Dp, D)
+        zo = restated.embed(feats, k, s, Dp, D)
+        assert zr.shape == zo.shape, (case, zr.shape, zo.shape)
+        assert (zr - zo).abs().max().item() <= 5e-6, (case, k, s, [tuple(f.shape) for f in feats], Dp, D)
+    for case in range(8):
+        N, P, Dd = int(rng.integers(2, 6)), int(rng.integers(4, 30)), int(rng.integers(8, 40))
+        Z = torch.randn(N, P, Dd, generator=gen) * float(rng.uniform(0.5, 3.0))
+        Zt = torch.randn(int(rng.integers(1, 5)), P, Dd, generator=gen)
+        tau = float(rng.choice([0.0, 0.3, 1.0, 2.5, 20.0]))
+        assert (ref_import.reference_alpha_unsupervised(tau, Z) - restated.matrix_alpha_unsupervised(tau, Z)).abs().max().item() <= 1e-6
+        assert (ref_import.reference_alpha_supervised(tau, Z, Zt) - restated.matrix_alpha_supervised(tau, Z, Zt)).abs().max().item() <= 1e-6
