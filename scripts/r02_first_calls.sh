@@ -5,6 +5,8 @@
 N=${1:-8}
 OUT=gpurun_out/r02_first
 mkdir -p $OUT
+# 0. single GPU: random-geometry fuzz of ac_embed against the oracle (promote into tests/ once green)
+timeout 200 python scripts/fuzz_embed_gpu.py 60 > $OUT/fuzz_embed.log 2>&1; echo "fuzz embed rc=$?"; tail -3 $OUT/fuzz_embed.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 # 1. bit-identity of the shard-granular NCCL pipeline (and the default schedules) against one GPU
 timeout 150 $TR --master-port 29551 scripts/check_sharded.py > $OUT/check_pipeline_n$N.log 2>&1; echo "check pipeline rc=$?"
