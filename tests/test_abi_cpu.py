@@ -116,3 +116,20 @@ def test_plain_c_program_links_the_abi(lib_path, tmp_path):
         assert r.returncode == 0, r.stdout
     else:
         assert r.returncode == 2 and "no sm_100 device" in r.stdout
+
+
+def test_header_is_valid_c99_and_cxx(tmp_path):
+    """include/ac_b200.h on its own, as strict C99 and as C++17, with warnings as errors: the boundary a non-Python
+    consumer compiles against must not depend on anything but <stddef.h>/<stdint.h> and the CUDA runtime header."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("no C toolchain / CUDA headers")
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"]
+    c = tmp_path / "t.c"
+    c.write_text('#include "ac_b200.h"\nint main(void) { int (*f)(void) = ac_version; (void)f; return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-fsyntax-only", str(c)] + inc, check=True)
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "ac_b200.h"\nint main() { int (*f)() = ac_version; (void)f; return 0; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-fsyntax-only", str(cpp)] + inc, check=True)
