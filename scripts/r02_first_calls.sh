@@ -18,6 +18,8 @@ AC_SHARD_PIPELINE=1 timeout 120 $TR --master-port 29554 bench.py --gpus $N --ste
 AC_SHARD_PIPELINE=1 AC_SHARD_TRANSPORT=symm timeout 120 $TR --master-port 29555 bench.py --gpus $N --steps 20 --warmup 5 --no-e2e > $OUT/bench_symm_n$N.json 2> $OUT/bench_symm_n$N.err
 # 4. sharded supervised path at N ranks (validated at 1 and 2 ranks in round 1)
 timeout 150 $TR --master-port 29556 scripts/check_supervised_sharded.py > $OUT/check_supervised_n$N.log 2>&1; echo "check supervised rc=$?"
+# 5. configs 3 and 5 at N ranks (1-GPU numbers: scripts/run_configs.py)
+timeout 240 $TR --master-port 29557 scripts/run_configs_sharded.py > $OUT/configs_n$N.log 2>&1; echo "configs rc=$?"; tail -1 $OUT/configs_n$N.log
 grep -h "OK\|MISMATCH" $OUT/check_*_n$N.log | tail -40
 for f in $OUT/bench_*_n$N.json; do python - "$f" <<'PY'
 import json, sys
