@@ -133,3 +133,33 @@ def test_header_is_valid_c99_and_cxx(tmp_path):
     cpp = tmp_path / "t.cpp"
     cpp.write_text('#include "ac_b200.h"\nint main() { int (*f)() = ac_version; (void)f; return 0; }\n')
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-fsyntax-only", str(cpp)] + inc, check=True)
+
+
+def test_mirror_surface_never_computes_on_cpu(lib_path):
+    """Every compute entry point of the reference-facing mirror refuses CPU tensors instead of quietly running
+    torch on the host: the product has no CPU path (the oracle is test infrastructure only)."""
+    import torch
+
+    from anomaly_clustering_b200 import ops, pipeline
+    from anomaly_clustering_b200.patchcore import common, patchcore, utils
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    x = torch.zeros(2, 6, 5, 5)
+    Z = torch.zeros(3, 25, 16)
+    calls = [
+        lambda: common.MeanMapper(8)(x),
+        lambda: common.Preprocessing([54, 54], 8)([x, x]),
+        lambda: common.Aggregator(8)(torch.zeros(4, 2, 8)),
+        lambda: patchcore.PatchMaker(3, stride=1).patchify(x),
+        lambda: utils.Matrix_Alpha_Unsupervised(1.0, 1, Z, torch.device("cpu")),
+        lambda: utils.Matrix_Alpha_Supervised(1.0, 1, Z, Z, torch.device("cpu")),
+        lambda: utils.Weight_Distance_Unsupervised(Z, 0, torch.device("cpu")),
+        lambda: pipeline.run_path([x, x], 3, 1, 8, 16),
+        lambda: ops.embed([x], 3, 1, 8, 16),
+        lambda: ops.alpha(torch.zeros(2, 4), [1.0]),
+        lambda: ops.weighted_embed(torch.zeros(3, 25), Z),
+    ]
+    for call in calls:
+        with pytest.raises(ValueError, match="CUDA tensors only"):
+            call()
