@@ -58,8 +58,15 @@ def load_peaks():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / power / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).
+    The sampler is started BEFORE the warm-up steps (nvidia-smi needs a few hundred ms before its first line) and
+    the samples are cut to the timed window by their timestamps; when the timed region is shorter than two
+    sampling periods the under-load samples of warm-up + timed region are used and `window` says so.
+    Never raises: a failure is reported inside the record."""
+
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 50
 
     def __init__(self, gpu_index: int):
         self.proc = None
@@ -68,37 +75,66 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", str(self.PERIOD_MS)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, pw, reasons = [], [], [], set()
+    @staticmethod
+    def parse(out: str):
+        """-> list of (epoch seconds | None, sm MHz, max sm MHz, power W, set of active slowdown reasons)."""
+        import datetime
+
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                sm, mx, pw = float(f[2]), float(f[3]), float(f[4])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = None
+            reasons = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10])
+                       if v.lower().startswith("active")}
+            rows.append((ts, sm, mx, pw, reasons))
+        return rows
+
+    @staticmethod
+    def summarise(rows, t_begin=None, t_end=None):
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        window = "timed region"
+        sel = [r for r in rows if r[0] is not None and t_begin is not None and t_begin <= r[0] <= t_end]
+        if len(sel) < 2:
+            # timed region shorter than two sampling periods (or no usable timestamps): under-load samples of the
+            # whole run of the sampler (warm-up + timed region, same kernels back to back)
+            top = max(r[3] for r in rows)
+            sel = [r for r in rows if r[3] > 0.5 * top] or rows
+            window = "warm-up + timed region (under-load samples; timed region shorter than 2 sampling periods)"
+        reasons = set()
+        for r in sel:
+            reasons |= r[4]
+        return {"sm_mhz": statistics.median(r[1] for r in sel), "sm_max_mhz": max(r[2] for r in sel),
+                "power_w_max": max(r[3] for r in sel), "samples": len(sel), "window": window, "reasons": sorted(reasons)}
+
+    def stop(self, t_begin=None, t_end=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        try:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            return self.summarise(self.parse(out), t_begin, t_end)
+        except Exception as e:   # noqa: BLE001 -- the clocks record must never take the bench line down
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler error: %r" % (e,)]}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -233,26 +269,28 @@ def main():
             torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-resident timing
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # before the warm-up: nvidia-smi is slow to emit its first line
     for _ in range(args.warmup):
         step(feats)
     sync_all()
     pipeline.PROFILE = []
     launches0 = ops.launches()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     if args.cuda_profiler:
         torch.cuda.profiler.start()
+    t_begin = time.time()
     ev0.record()
     for _ in range(args.steps):
         out = step(feats)
     ev1.record()
     sync_all()
+    t_end = time.time()
     if args.cuda_profiler:
         torch.cuda.profiler.stop()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches = ops.launches() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
     marks = pipeline.PROFILE
