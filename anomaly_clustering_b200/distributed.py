@@ -489,6 +489,20 @@ def run_path_sharded_supervised(
     return a64, X_all, Dm, w
 
 
+def run_path_sharded_average(local_features: Sequence[torch.Tensor], n_total: int, patchsize: int, stride: int, pretrain_dim: int,
+                             target_dim: int, group=None):
+    """'average' mode (examples/main.py:290-291: alpha = 1/P) sharded by query image: every rank reduces its own images,
+    the X rows are all-gathered, Dmat on every rank.  Returns (X_all [1,N,D], Dmat [1,N,N])."""
+    from . import ops, pipeline
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    bounds = shard_bounds(n_total, world)
+    r = pipeline.run_path(local_features, patchsize, stride, pretrain_dim, target_dim, "average", keep_z=False)
+    assert r.X.shape[1] == bounds[rank][1] - bounds[rank][0]
+    X_all = all_gather_rows(r.X[0], [b - a for a, b in bounds], group)
+    return X_all.unsqueeze(0), ops.pairwise_l2(X_all).unsqueeze(0)
+
+
 def run_categories_sharded(sizes: Sequence[int], run_category, group=None):
     """Per-category banks (the reference's own semantics: one make_category_data per category, main.py:353):
     whole categories are assigned to ranks by greedy LPT on n_c * (n_c - 1) (the pair count)

@@ -234,3 +234,25 @@ def run_path(
     a64, a32, X, Dm = alpha_X_dist(q, w, list(taus), features, (patchsize, stride, pretrain_dim, layernorm))
     return PathResult(Z=None if q.Z is None else q.Z.reshape(q.n_img, q.P, q.D), w=w, alpha64=a64, alpha32=a32, X=X, Dmat=Dm,
                       taus=list(taus), grid=q.grid)
+
+
+def run_categories(
+    features: Sequence[torch.Tensor],
+    sizes: Sequence[int],
+    patchsize: int = 3,
+    stride: int = 1,
+    pretrain_dim: int = 1024,
+    target_dim: int = 1024,
+    taus: Sequence[float] = (1.0,),
+    precision: str = "auto",
+    keep_z: bool = True,
+) -> List[PathResult]:
+    """Several independent categories (the reference's own semantics: one make_category_data per category, each with
+    its own bank -- examples/main.py:353) from ONE batch of hooked features: `features` hold the images of all
+    categories back to back, `sizes[c]` images each.  Returns one PathResult per category."""
+    out, start = [], 0
+    for n in sizes:
+        out.append(run_path([f[start:start + n] for f in features], patchsize, stride, pretrain_dim, target_dim, "unsupervised",
+                            taus, precision=precision, keep_z=keep_z))
+        start += n
+    return out

@@ -19,11 +19,15 @@ def planted_features(
     device="cpu",
     defect_gain: float = 3.0,
     noise: float = 1.0,
+    channel_bias: float = 0.0,
 ):
     """layers: [(C, H, W, tokens)] -> (list of per-layer feature tensors, labels [n_img]).
 
     tokens=True yields ViT block outputs [N, 1+H*W, C] (CLS first), else CNN maps [N,C,H,W].
-    Class 0 is 'good'; class c>0 plants a defect block whose channel signature depends on c."""
+    Class 0 is 'good'; class c>0 plants a defect block whose channel signature depends on c.
+    channel_bias > 0 adds a fixed per-channel offset N(0, channel_bias^2) to every image and position (real
+    ViT features carry strong per-channel means): it survives the pooling, so the patch norms grow (45-50 at
+    1.45 for the config-2 shape) while the patch DISTANCES shrink -- the hard case for the |x|^2+|y|^2-2xy form."""
     gen = torch.Generator(device="cpu").manual_seed(seed)
     labels = torch.arange(n_img) % n_classes
     # defect geometry is shared across layers (relative coordinates)
@@ -37,6 +41,8 @@ def planted_features(
         template = (u @ v).reshape(1, C, H, W) / rank ** 0.5
         x = template + noise * torch.randn(n_img, C, H, W, generator=gen)
         sig = torch.randn(n_classes, C, generator=gen)
+        if channel_bias:
+            x = x + channel_bias * torch.randn(C, generator=gen).reshape(1, C, 1, 1)
         for i in range(n_img):
             c = int(labels[i])
             if c == 0:
@@ -71,6 +77,7 @@ def planted_features_device(
     seed: int = 2023,
     device="cuda",
     defect_gain: float = 3.0,
+    channel_bias: float = 0.0,
 ):
     """Same construction as planted_features, generated directly on the device per GLOBAL image id
     (so any rank can produce exactly its slice of a fixed synthetic data set).  Used by bench.py."""
@@ -84,6 +91,8 @@ def planted_features_device(
         v = torch.randn(rank, H * W, generator=g, device=dev)
         template = (u @ v).reshape(C, H, W) / rank ** 0.5
         sig = torch.randn(n_classes, C, generator=g, device=dev)
+        if channel_bias:
+            template = template + channel_bias * torch.randn(C, generator=g, device=dev).reshape(C, 1, 1)
         T = (1 + H * W) if tokens else 0
         out = torch.empty((len(ids), T, C) if tokens else (len(ids), C, H, W), dtype=torch.float32, device=dev)
         for n, i in enumerate(ids):

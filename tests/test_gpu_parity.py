@@ -402,52 +402,4 @@ def test_tau_sweep_reuses_one_distance_pass():
         assert rel_l2(res.X[i].cpu().numpy(), restated.weighted_embedding(a, Z)) <= 1e-3
 
 
-# ------------------------------------------------------------------------------- full BASELINE sizes
-def test_config2_full_size_properties():
-    """BASELINE config 2 at full size (100 images x 784 patches x 4096-d): too large for the CPU oracle, so
-    checked through size-independent properties: the symmetric kernel (each image pair once) equals the
-    all-pairs kernel, results are bit-reproducible (min-reductions only), alpha rows sum to 1, Dmat is a
-    symmetric zero-diagonal matrix that satisfies the triangle inequality, and a permutation of the images
-    permutes the outputs."""
-    layers = [(768, 28, 28, True), (768, 28, 28, True)]
-    feats, labels = synth.planted_features_device(range(100), layers, device="cuda")
-    try:
-        pipeline.SYMMETRIC = True
-        r1 = pipeline.run_path(feats, 3, 1, 2048, 4096, "unsupervised", [1.0, 2.0])
-        r1b = pipeline.run_path(feats, 3, 1, 2048, 4096, "unsupervised", [1.0, 2.0])
-        pipeline.SYMMETRIC = False
-        r2 = pipeline.run_path(feats, 3, 1, 2048, 4096, "unsupervised", [1.0, 2.0])
-    finally:
-        pipeline.SYMMETRIC = True
-    assert torch.equal(r1.w, r1b.w) and torch.equal(r1.Dmat, r1b.Dmat)
-    assert ((r1.w - r2.w).abs() / r2.w).max().item() <= 2e-4
-    assert (r1.alpha64 - r2.alpha64).abs().max().item() <= 1e-3
-    assert (r1.alpha64.sum(dim=2) - 1).abs().max().item() <= 1e-12
-    D = r1.Dmat[0]
-    assert torch.equal(D, D.T) and (D.diagonal() == 0).all() and (D >= 0).all()
-    assert (D[:, None, :] <= D[:, :, None] + D[None, :, :] + 1e-3).all()        # triangle inequality
-    # permutation equivariance (unsupervised weights depend on the SET of other images only)
-    perm = torch.randperm(100, generator=torch.Generator().manual_seed(0)).cuda()
-    r3 = pipeline.run_path([f[perm] for f in feats], 3, 1, 2048, 4096, "unsupervised", [1.0])
-    assert ((r3.w - r1.w[perm]).abs() / r1.w[perm]).max().item() <= 2e-4
-    assert (r3.X[0] - r1.X[0][perm]).norm().item() / r1.X[0].norm().item() <= 1e-3
-    # the planted classes are recovered from the GPU distance matrix
-    from anomaly_clustering_b200 import cluster
-
-    nmi, ari, f1, _, _ = cluster.calculate_metrics(D.cpu().numpy(), [str(int(c)) for c in labels])
-    assert nmi > 0.9
-
-
-def test_config5_geometry_tau_sweep():
-    """BASELINE config 5 geometry at reduced image count: ViT-S/8 tokens at 448x448 (3136 patches), six taus
-    from one distance pass; the 13-tile bank images (12 x 256 + 64) against the exact SIMT kernel."""
-    layers = [(384, 56, 56, True), (384, 56, 56, True)]
-    feats, _ = synth.planted_features_device(range(5), layers, device="cuda")
-    taus = [0.1, 0.5, 1.0, 2.0, 5.0, 10.0]
-    r = pipeline.run_path(feats, 3, 1, 2048, 4096, "unsupervised", taus, precision="f16x3")
-    ex = pipeline.run_path(feats, 3, 1, 2048, 4096, "unsupervised", taus, precision="f32")
-    assert r.w.shape == (5, 3136)
-    assert ((r.w - ex.w).abs() / ex.w).max().item() <= 5e-4
-    for t in range(1, len(taus)):      # tau >= 0.5 within the north-star alpha tolerance
-        assert (r.alpha64[t] - ex.alpha64[t]).abs().max().item() <= 1e-3
-    assert (r.alpha64.sum(dim=2) - 1).abs().max().item() <= 1e-12
+# The full BASELINE sizes (configs 1, 2, 3, 5 against the oracle) live in tests/test_gpu_baseline_sizes.py.
