@@ -20,7 +20,9 @@ AC_DT_F32, AC_DT_F16, AC_DT_BF16 = 0, 1, 2
 AC_PREC_F16, AC_PREC_BF16, AC_PREC_F16X3, AC_PREC_BF16X3, AC_PREC_F32 = 0, 1, 2, 3, 4
 AC_REDUCE_MEAN, AC_REDUCE_MIN = 0, 1
 
-PRECISIONS = {"f16": AC_PREC_F16, "bf16": AC_PREC_BF16, "f16x3": AC_PREC_F16X3, "bf16x3": AC_PREC_BF16X3, "f32": AC_PREC_F32}
+PRECISIONS = {"f16": AC_PREC_F16, "bf16": AC_PREC_BF16, "f16x3": AC_PREC_F16X3, "bf16x3": AC_PREC_BF16X3, "f32": AC_PREC_F32,
+              # "r" modes: one tensor-core pass that also records the arg-min + exact fp32 re-evaluation (ac_refine_min_dist)
+              "f16r": AC_PREC_F16, "bf16r": AC_PREC_BF16}
 
 
 class AcLayer(ctypes.Structure):
@@ -68,6 +70,21 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
          c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+    "ac_min_dist_arg": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+         c_size_t, c_void_p],
+    ),
+    "ac_min_dist_sym_arg": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+         c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
+    "ac_refine_min_dist": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+         c_void_p, c_int, c_void_p, c_void_p],
     ),
     "ac_reduce_weights_sym": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ac_reduce_weights": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),

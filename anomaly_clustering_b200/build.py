@@ -18,7 +18,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "csrc", "build")
 LIB = os.path.join(PKG, "libac_b200.so")
-SOURCES = ["embed.cu", "mindist_simt.cu", "mindist_tc.cu", "stage3.cu"]
+SOURCES = ["embed.cu", "mindist_simt.cu", "mindist_tc.cu", "refine.cu", "stage3.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

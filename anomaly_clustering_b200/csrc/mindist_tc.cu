@@ -66,6 +66,9 @@ struct __align__(64) TcParams {
   int win_begin, win_count;  // sym mode: only bank images in the circular window [win_begin, win_begin + win_count)
   int dynamic;               // 1: units are claimed from a global counter (work stealing) instead of round-robin
   unsigned long long* counter;
+  // arg-min tracking (kArg kernels; the exact re-evaluation of ac_refine_min_dist needs WHICH bank row won)
+  int* rowarg;                   // [nb_img, Mq] row inside bank image j that is nearest to query row r
+  unsigned long long* colkey;    // sym: [nq_img, nb_img*P] (fp32 bits of d2 << 32) | row inside the query image, atomicMin target
 };
 
 // Ownership of the unordered pair {i, j} of N images: the image that sees the other one within the
@@ -289,6 +292,22 @@ __device__ __forceinline__ float warp_transpose_min(float (&r)[32], int lane) {
   return r[0];
 }
 
+// same butterfly on 64-bit keys (distance bits << 32 | row): the min carries the arg-min with it
+__device__ __forceinline__ unsigned long long warp_transpose_min_u64(unsigned long long (&r)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const unsigned long long keep = up ? r[i + off] : r[i];
+      const unsigned long long send = up ? r[i] : r[i + off];
+      const unsigned long long got = __shfl_xor_sync(0xffffffffu, send, off);
+      r[i] = keep < got ? keep : got;
+    }
+  }
+  return r[0];
+}
+
 template <int G>
 __device__ __forceinline__ bool decode_unit(const TcParams& p, long long u, int& mb, int& img) {
   if (p.sym) {
@@ -311,7 +330,7 @@ __device__ __forceinline__ bool decode_unit(const TcParams& p, long long u, int&
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int G, int kStages>
+template <int G, int kStages, bool kArg>
 __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int kBRows = kMaxN / G;                         // bank rows staged per CTA per stage
   constexpr uint32_t kABytes = kTileM * kBlockK * 2;        // 16 KB
@@ -510,11 +529,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
       const int ilo = p.q_img0 + (int)(min(wrow0, p.Mq - 1) / p.P);
       const int ihi = p.q_img0 + (int)(min(wrow0 + 31, p.Mq - 1) / p.P);
       float best = INFINITY;
+      int bestc = 0;                                        // kArg: column (row inside bank image img) of the running min
+      // kArg, sym: this row's index inside its query image rides in the low half of the column-min keys
+      const unsigned int rin = (unsigned int)((rvalid ? row : 0) - (long long)(irow - p.q_img0) * p.P);
       for (int t = 0; t < p.nt; ++t, ++tile_ctr) {
         const uint32_t buf = tile_ctr & 1, tphase = (tile_ctr >> 1) & 1;
         const int width = (t == p.nt - 1) ? p.wlast : p.wmain;
         const int valid = min(width, p.P - t * p.wmain);
-        const long long col0 = (long long)img * p.P + t * p.wmain;
+        const int cbase = t * p.wmain;
+        const long long col0 = (long long)img * p.P + cbase;
         float* bn = s_bn2 + buf * kMaxN;
         for (int c = eidx; c < width; c += 128) bn[c] = (c < valid) ? __ldg(p.bn2 + col0 + c) : INFINITY;
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -529,10 +552,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
           tmem_ld_wait();
           if (!p.sym) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) best = fminf(best, fmaf(-2.f, __uint_as_float(v0[i]), bn[c0 + i]));
+            for (int i = 0; i < 16; ++i) {
+              const float part = fmaf(-2.f, __uint_as_float(v0[i]), bn[c0 + i]);
+              if (kArg) { if (part < best) { best = part; bestc = cbase + c0 + i; } }
+              else best = fminf(best, part);
+            }
             if (two) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) best = fminf(best, fmaf(-2.f, __uint_as_float(v1[i]), bn[c0 + 16 + i]));
+              for (int i = 0; i < 16; ++i) {
+                const float part = fmaf(-2.f, __uint_as_float(v1[i]), bn[c0 + 16 + i]);
+                if (kArg) { if (part < best) { best = part; bestc = cbase + c0 + 16 + i; } }
+                else best = fminf(best, part);
+              }
             }
           } else {
             // row-min as above + column-min over the 32 rows of this warp.  A butterfly "transpose
@@ -543,14 +574,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float part = fmaf(-2.f, __uint_as_float(v0[i]), bn[c0 + i]);
-              best = fminf(best, part);
+              if (kArg) { if (part < best) { best = part; bestc = cbase + c0 + i; } }
+              else best = fminf(best, part);
               e[i] = fmaxf(part + qn, 0.f);
             }
             if (two) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float part = fmaf(-2.f, __uint_as_float(v1[i]), bn[c0 + 16 + i]);
-                best = fminf(best, part);
+                if (kArg) { if (part < best) { best = part; bestc = cbase + c0 + 16 + i; } }
+                else best = fminf(best, part);
                 e[16 + i] = fmaxf(part + qn, 0.f);
               }
             } else {
@@ -559,21 +592,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
             }
             const bool in_lo = act && (irow == ilo), in_hi = act && (irow == ihi) && (ihi != ilo);
             const int c = c0 + lane;
-            {
-              float r[32];
+            if (!kArg) {
+              {
+                float r[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = in_lo ? e[i] : INFINITY;
-              const float m = warp_transpose_min(r, lane);
-              if (c < valid && m < 3.0e38f)
-                atomicMin(p.colmin + (long long)(ilo - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, __float_as_uint(m));
-            }
-            if (ihi != ilo) {   // warp-uniform: this warp's rows straddle two query images
-              float r[32];
+                for (int i = 0; i < 32; ++i) r[i] = in_lo ? e[i] : INFINITY;
+                const float m = warp_transpose_min(r, lane);
+                if (c < valid && m < 3.0e38f)
+                  atomicMin(p.colmin + (long long)(ilo - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, __float_as_uint(m));
+              }
+              if (ihi != ilo) {   // warp-uniform: this warp's rows straddle two query images
+                float r[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = in_hi ? e[i] : INFINITY;
-              const float m = warp_transpose_min(r, lane);
-              if (c < valid && m < 3.0e38f)
-                atomicMin(p.colmin + (long long)(ihi - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, __float_as_uint(m));
+                for (int i = 0; i < 32; ++i) r[i] = in_hi ? e[i] : INFINITY;
+                const float m = warp_transpose_min(r, lane);
+                if (c < valid && m < 3.0e38f)
+                  atomicMin(p.colmin + (long long)(ihi - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, __float_as_uint(m));
+              }
+            } else {
+              // same reduction on (distance bits << 32 | row inside the query image): the winner names its row
+              constexpr unsigned long long kNone = ~0ull;
+              {
+                unsigned long long r[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  r[i] = (in_lo && e[i] < 3.0e38f) ? (((unsigned long long)__float_as_uint(e[i]) << 32) | rin) : kNone;
+                const unsigned long long m = warp_transpose_min_u64(r, lane);
+                if (c < valid && m != kNone)
+                  atomicMin(p.colkey + (long long)(ilo - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, m);
+              }
+              if (ihi != ilo) {
+                unsigned long long r[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  r[i] = (in_hi && e[i] < 3.0e38f) ? (((unsigned long long)__float_as_uint(e[i]) << 32) | rin) : kNone;
+                const unsigned long long m = warp_transpose_min_u64(r, lane);
+                if (c < valid && m != kNone)
+                  atomicMin(p.colkey + (long long)(ihi - p.q_img0) * ((long long)p.nb_img * p.P) + col0 + c, m);
+              }
             }
           }
         }
@@ -587,6 +643,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
       if (act) {
         const float d2 = fmaxf(best + qn, 0.f);
         p.dmin[(long long)img * p.Mq + row] = p.sym ? d2 : sqrtf(d2);
+        if (kArg) p.rowarg[(long long)img * p.Mq + row] = bestc;
       }
     }
   }
@@ -711,12 +768,12 @@ static int g_tc_dynamic = 1;  // knob 4: dynamic unit scheduler (work stealing);
 static int g_tc_l2hint = 0;  // debug knob 3: L2 evict_last policy on operand loads (measured: no gain, off)
 static int g_tc_gm = 16;  // query blocks per raster group: 16 x 2 MB of A + the streaming bank images stay L2-resident (tuned on B200)
 
-template <int G, int kStages>
+template <int G, int kStages, bool kArg>
 static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {
   constexpr int kBRows = kMaxN / G;
   constexpr size_t kStageBytes = (size_t)kTileM * kBlockK * 2 + (size_t)kBRows * kBlockK * 2;
   const size_t smem = 1024 + kStages * kStageBytes + 2 * kMaxN * sizeof(float) + (2 * kStages + 4) * 8 + 256;
-  auto kern = mindist_tc_kernel<G, kStages>;
+  auto kern = mindist_tc_kernel<G, kStages, kArg>;
   AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long max_workers = (G == 2) ? num_sms / 2 : num_sms;
   const int workers = (int)std::min<long long>(max_workers, prm.total_units);
@@ -740,7 +797,7 @@ static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {
 int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long long Mq, const void* Bhi, const void* Blo,
                       const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int* err_flag, cudaStream_t st,
                       int sym = 0, int q_img0 = 0, unsigned int* colmin = nullptr, void* unit_ws = nullptr, size_t unit_ws_bytes = 0,
-                      int win_begin = 0, int win_count = -1) {
+                      int win_begin = 0, int win_count = -1, int* rowarg = nullptr, unsigned long long* colkey = nullptr) {
   const bool bf16 = (precision == AC_PREC_BF16 || precision == AC_PREC_BF16X3);
   const bool x3 = (precision == AC_PREC_F16X3 || precision == AC_PREC_BF16X3);
   if (D % 8 != 0) return AC_ERR_UNSUPPORTED;  // TMA needs a 16-byte row pitch
@@ -764,6 +821,9 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.dynamic = g_tc_dynamic;
   prm.counter = (unsigned long long*)((char*)err_flag + 128);   // inside the zeroed 256-byte workspace header
   prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin; prm.units = nullptr;
+  prm.rowarg = rowarg; prm.colkey = colkey;
+  const bool arg = (rowarg != nullptr);
+  if (arg && sym && !colkey) return AC_ERR_INVALID;
   prm.win_begin = win_begin; prm.win_count = (win_count < 0) ? nb_img : win_count;
   // bank images a raster group of GM query blocks can own: N/2 after each of the images it spans
   prm.KU = std::min(nb_img, nb_img / 2 + (int)(((long long)prm.GM * kTileM * G - 1) / P) + 1);
@@ -799,8 +859,8 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   int dev = 0, num_sms = 0;
   AC_CUDA(cudaGetDevice(&dev));
   AC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  if (G == 2) return launch_tc<2, 6>(prm, num_sms, st);
-  return launch_tc<1, 4>(prm, num_sms, st);
+  if (G == 2) return arg ? launch_tc<2, 6, true>(prm, num_sms, st) : launch_tc<2, 6, false>(prm, num_sms, st);
+  return arg ? launch_tc<1, 4, true>(prm, num_sms, st) : launch_tc<1, 4, false>(prm, num_sms, st);
 }
 
 int launch_mindist_simt(const float* Q, long long Mq, const float* Bk, int nb_img, int P, int D, float* dmin, cudaStream_t st);
@@ -811,8 +871,10 @@ using namespace ac;
 
 // test / tuning hook (not part of the public header): key 0 = cta group (1|2), key 1 = M-blocks per raster group
 extern "C" int ac_debug_set_embed(int value);
+extern "C" int ac_debug_set_refine(int mb);
 extern "C" int ac_debug_set(int key, int value) {
   if (key == 2) return ac_debug_set_embed(value);
+  if (key == 5) return ac_debug_set_refine(value);
   if (key == 0 && (value == 1 || value == 2)) { g_tc_cta_group = value; return AC_OK; }
   if (key == 1 && value >= 1) { g_tc_gm = value; return AC_OK; }
   if (key == 3 && (value == 0 || value == 1)) { g_tc_l2hint = value; return AC_OK; }
@@ -836,11 +898,13 @@ __global__ void reduce_weights_sym_kernel(const float* __restrict__ rowmin, cons
   w[r] = cnt > 0 ? s / (float)cnt : nanf("");
 }
 
-extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
-                               const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
-                               int bank_count, int init_colmin, float* rowmin_d2, float* colmin_d2, void* ws, size_t ws_bytes,
-                               ac_stream_t stream) {
-  if (!Qhi || !Bhi || !Qn2 || !Bn2 || !rowmin_d2 || !colmin_d2 || Mq < 0 || nb_img < 1 || P < 1 || D < 1 || q_img0 < 0)
+static int min_dist_sym_impl(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                             const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                             int bank_count, int init_colmin, float* rowmin_d2, float* colmin_d2, int32_t* rowarg, uint64_t* colkey,
+                             void* ws, size_t ws_bytes, ac_stream_t stream) {
+  const bool arg = (rowarg != nullptr);
+  if (!Qhi || !Bhi || !Qn2 || !Bn2 || !rowmin_d2 || (!arg && !colmin_d2) || (arg && !colkey) || Mq < 0 || nb_img < 1 || P < 1 ||
+      D < 1 || q_img0 < 0)
     return AC_ERR_INVALID;
   if (bank_begin < 0 || bank_begin >= nb_img || bank_count < 0 || bank_count > nb_img) return AC_ERR_INVALID;
   if (precision < AC_PREC_F16 || precision > AC_PREC_BF16X3) return AC_ERR_UNSUPPORTED;  // tensor-core modes only
@@ -853,13 +917,32 @@ extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn
   cudaStream_t st = (cudaStream_t)stream;
   // column minima are accumulated with atomicMin on the fp32 bit pattern: start from a huge finite value
   if (init_colmin) {
-    const long long words = (long long)(Mq / P) * nb_img * P;
+    // float minima: one word per entry; (distance, row) keys: two words per entry -- same byte pattern, huge and finite
+    const long long words = (long long)(Mq / P) * nb_img * P * (arg ? 2 : 1);
     const int blocks = (int)std::min<long long>((words + 1023) / 1024, 148LL * 8);
-    fill_u32_kernel<<<blocks, 256, 0, st>>>((unsigned int*)colmin_d2, words, 0x7f7f7f7fu);
+    fill_u32_kernel<<<blocks, 256, 0, st>>>(arg ? (unsigned int*)colkey : (unsigned int*)colmin_d2, words, 0x7f7f7f7fu);
     AC_LAUNCH_CHECK();
   }
   return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, rowmin_d2, (int*)ws, st, 1, q_img0,
-                           (unsigned int*)colmin_d2, (char*)ws + 256, ws_bytes - 256, bank_begin, bank_count);
+                           (unsigned int*)colmin_d2, (char*)ws + 256, ws_bytes - 256, bank_begin, bank_count, rowarg,
+                           (unsigned long long*)colkey);
+}
+
+extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                               const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                               int bank_count, int init_colmin, float* rowmin_d2, float* colmin_d2, void* ws, size_t ws_bytes,
+                               ac_stream_t stream) {
+  return min_dist_sym_impl(Qhi, Qlo, Qn2, Mq, q_img0, Bhi, Blo, Bn2, nb_img, P, D, precision, bank_begin, bank_count, init_colmin,
+                           rowmin_d2, colmin_d2, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int ac_min_dist_sym_arg(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                                   const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                                   int bank_count, int init_colkey, float* rowmin_d2, int32_t* rowarg, uint64_t* colkey, void* ws,
+                                   size_t ws_bytes, ac_stream_t stream) {
+  if (!rowarg || !colkey) return AC_ERR_INVALID;
+  return min_dist_sym_impl(Qhi, Qlo, Qn2, Mq, q_img0, Bhi, Blo, Bn2, nb_img, P, D, precision, bank_begin, bank_count, init_colkey,
+                           rowmin_d2, nullptr, rowarg, colkey, ws, ws_bytes, stream);
 }
 
 extern "C" int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
@@ -881,10 +964,11 @@ extern "C" size_t ac_min_dist_workspace_bytes(int64_t Mq, int nb_img, int P, int
   return 256 + 16 + (size_t)(mblocks * per_mb) * sizeof(int2);
 }
 
-extern "C" int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
-                           const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, void* ws, size_t ws_bytes,
-                           ac_stream_t stream) {
+static int min_dist_impl(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
+                         const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int32_t* argmin, void* ws,
+                         size_t ws_bytes, ac_stream_t stream) {
   if (!Qhi || !Bhi || !dmin || Mq < 0 || nb_img < 1 || P < 1 || D < 1) return AC_ERR_INVALID;
+  if (argmin && precision == AC_PREC_F32) return AC_ERR_UNSUPPORTED;   // the exact kernel needs no refinement
   if (precision < AC_PREC_F16 || precision > AC_PREC_F32) return AC_ERR_INVALID;
   int rc = check_device();
   if (rc) return rc;
@@ -896,5 +980,19 @@ extern "C" int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, i
   if (!ws || ws_bytes < 256) return AC_ERR_WORKSPACE;
   fill_u32_kernel<<<1, 64, 0, st>>>((unsigned int*)ws, 64, 0u);   // watchdog flag (no copy-engine memset)
   AC_LAUNCH_CHECK();
-  return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, dmin, (int*)ws, st);
+  return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, dmin, (int*)ws, st, 0, 0, nullptr, nullptr, 0, 0,
+                           -1, argmin, nullptr);
+}
+
+extern "C" int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
+                           const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, void* ws, size_t ws_bytes,
+                           ac_stream_t stream) {
+  return min_dist_impl(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, dmin, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int ac_min_dist_arg(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
+                               const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int32_t* argmin, void* ws,
+                               size_t ws_bytes, ac_stream_t stream) {
+  if (!argmin) return AC_ERR_INVALID;
+  return min_dist_impl(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, dmin, argmin, ws, ws_bytes, stream);
 }

@@ -276,6 +276,9 @@ def run_path_sharded(
             supports_bank_window = True
             weighted_embed_from_features = staticmethod(ops.weighted_embed_from_features)
             reduce_weights_sym = staticmethod(ops.reduce_weights_sym)
+            min_dist_sym_arg = staticmethod(ops.min_dist_sym_arg)
+            refine_min_dist = staticmethod(ops.refine_min_dist)
+            reduce_weights = staticmethod(ops.reduce_weights)
 
         compute = _Cuda
 
@@ -292,11 +295,18 @@ def run_path_sharded(
     P = q.P
     row_counts = [(b - a) * P for a, b in bounds]
     use_sym = symmetric and precision != "f32" and P >= 32 and hasattr(compute, "min_dist_sym")
+    # refined modes ('f16r'): the tensor-core pass records arg-mins, ac_refine_min_dist re-evaluates the selected pairs
+    # exactly.  Every rank refines ALL (own row, other image) entries, so it needs the whole bank (full gather) and the
+    # (distance, row) keys of the column minima travel instead of the float minima.
+    refined = precision in pipeline.REFINED
+    if refined and not (use_sym and hasattr(compute, "min_dist_sym_arg")):
+        raise ValueError("precision %r needs the symmetric sharded path" % precision)
+    sym_launch = compute.min_dist_sym_arg if refined else compute.min_dist_sym
     pipeline._mark("gather_begin")
     pending = []
     pipeline_steps = None
     # opt-in (AC_SHARD_PIPELINE=1): shard-granular pipeline -- multiply against shard k while shards k+1.. travel
-    shard_pipeline = (use_sym and world > 2 and os.environ.get("AC_SHARD_PIPELINE", "0") == "1"
+    shard_pipeline = (use_sym and world > 2 and os.environ.get("AC_SHARD_PIPELINE", "0") == "1" and not refined
                       and getattr(compute, "supports_bank_window", False))
     if shard_pipeline:
         need_all = needed_shards(bounds, n_total)
@@ -313,7 +323,7 @@ def run_path_sharded(
     elif use_sym:
         # only the shards that hold bank images of pairs this rank owns (the next n_total//2 images);
         # the transfers stay in flight while the pairs inside the local shard are multiplied
-        if 3 <= world <= 4 or dist.get_backend(group) != "nccl":
+        if (3 <= world <= 4 or dist.get_backend(group) != "nccl") and not refined:
             # 3-4 ranks: point-to-point transfers of just the needed shards (about 2/3 of the volume).  At 2 ranks
             # the needed shard IS the other rank's shard and NCCL's all-gather moves it faster (0.5 vs 0.9 ms).
             need = needed_shards(bounds, n_total)
@@ -360,29 +370,35 @@ def run_path_sharded(
                                            bank_window=window, init=first, out=out)
                 pipeline._mark("mindist_end")
                 first = False
-            rowmin, colmin = out
         elif two_phase:
             # phase 1: bank images of the local shard (no remote data needed) overlaps the NCCL transfers
             pipeline._mark("mindist_begin")
-            out = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,
-                                       bank_window=(lo_i, q.n_img), init=True)
+            out = sym_launch(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,
+                             bank_window=(lo_i, q.n_img), init=True)
             pipeline._mark("mindist_end")
             for r in pending:
                 r.wait()
             pipeline._mark("mindist_begin")
-            rowmin, colmin = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,
-                                                  bank_window=(hi_i % n_total, n_total - q.n_img), init=False, out=out)
+            out = sym_launch(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,
+                             bank_window=(hi_i % n_total, n_total - q.n_img), init=False, out=out)
             pipeline._mark("mindist_end")
         else:
             for r in pending:
                 r.wait()
             pipeline._mark("mindist_begin")
-            rowmin, colmin = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision)
+            out = sym_launch(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision)
             pipeline._mark("mindist_end")
         pipeline._mark("exchange_begin")
-        colfull = exchange_colmin(colmin, bounds, P, group)
+        colfull = exchange_colmin(out[-1], bounds, P, group)       # float minima, or (distance, row) keys when refined
         pipeline._mark("exchange_end")
-        w = compute.reduce_weights_sym(rowmin, colfull, P, lo_i).reshape(q.n_img, P)
+        if refined:
+            pipeline._mark("refine_begin")
+            dex = compute.refine_min_dist(q.Z, q.hi, q.lo, bank.hi, bank.lo, n_total, P, out[1], colkey=colfull, q_img0=lo_i)
+            pipeline._mark("refine_end")
+            own = torch.arange(lo_i, hi_i, dtype=torch.int32, device=dex.device)
+            w = compute.reduce_weights(dex, P, own, "mean").reshape(q.n_img, P)
+        else:
+            w = compute.reduce_weights_sym(out[0], colfull, P, lo_i).reshape(q.n_img, P)
     else:
         q_self = torch.arange(lo_i, hi_i, dtype=torch.int32, device=q.hi.device if q.Z is None else q.Z.device)
         w = compute.min_distance_weights(q, bank, "unsupervised", precision, q_self=q_self)

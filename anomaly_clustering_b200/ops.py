@@ -191,6 +191,75 @@ def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int,
     return rowmin, colmin
 
 
+def min_dist_arg(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str):
+    """ac_min_dist_arg: (dmin [nb_img, Mq], argmin [nb_img, Mq] int32 = row inside bank image j nearest to query row r)."""
+    lib = _lib.load()
+    _need_cuda(Qhi, Bhi)
+    prec = _lib.PRECISIONS[precision]
+    Mq, D = Qhi.shape
+    assert Bhi.shape == (nb_img * P, D) and Qhi.is_contiguous() and Bhi.is_contiguous()
+    dmin = torch.empty(nb_img, Mq, dtype=torch.float32, device=Qhi.device)
+    arg = torch.empty(nb_img, Mq, dtype=torch.int32, device=Qhi.device)
+    ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
+    rc = lib.ac_min_dist_arg(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec, _ptr(dmin),
+                             _ptr(arg), _ptr(ws), ws_bytes, _stream())
+    check(rc, "ac_min_dist_arg")
+    return dmin, arg
+
+
+def min_dist_sym_arg(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str,
+                     bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None):
+    """ac_min_dist_sym_arg: (rowmin_d2 [nb_img, Mq], rowarg [nb_img, Mq] int32, colkey [Mq/P, nb_img*P] int64 =
+    (fp32 bits of the column minimum << 32) | row inside the query image).  Windows / accumulation as min_dist_sym."""
+    lib = _lib.load()
+    _need_cuda(Qhi, Bhi)
+    prec = _lib.PRECISIONS[precision]
+    Mq, D = Qhi.shape
+    assert Bhi.shape == (nb_img * P, D) and Qhi.is_contiguous() and Bhi.is_contiguous()
+    if out is None:
+        rowmin = torch.empty(nb_img, Mq, dtype=torch.float32, device=Qhi.device)
+        rowarg = torch.zeros(nb_img, Mq, dtype=torch.int32, device=Qhi.device)
+        colkey = torch.empty(Mq // P, nb_img * P, dtype=torch.int64, device=Qhi.device)
+    else:
+        rowmin, rowarg, colkey = out
+    begin, count = bank_window if bank_window is not None else (0, nb_img)
+    ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
+    rc = lib.ac_min_dist_sym_arg(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
+                                 int(begin), int(count), int(bool(init)), _ptr(rowmin), _ptr(rowarg), _ptr(colkey), _ptr(ws),
+                                 ws_bytes, _stream())
+    check(rc, "ac_min_dist_sym_arg")
+    return rowmin, rowarg, colkey
+
+
+def refine_min_dist(Zq: Optional[torch.Tensor], Qhi, Qlo, Bhi, Blo, nb_img: int, P: int, rowarg: torch.Tensor,
+                    colkey: Optional[torch.Tensor] = None, q_img0: int = 0, q_self: Optional[torch.Tensor] = None,
+                    Pq: Optional[int] = None) -> torch.Tensor:
+    """ac_refine_min_dist: exact fp32 distances [nb_img, Mq] of the (query row, selected bank row) pairs.
+    colkey given -> symmetric form (layout [nb_img, Mq], i.e. after the column-block exchange)."""
+    lib = _lib.load()
+    _need_cuda(Bhi, rowarg)
+    Mq = rowarg.shape[1]
+    D = Bhi.shape[1]
+    assert rowarg.shape == (nb_img, Mq) and rowarg.dtype == torch.int32 and rowarg.is_contiguous()
+    assert Bhi.shape == (nb_img * P, D) and Bhi.is_contiguous()
+    if Zq is not None:
+        assert Zq.shape == (Mq, D) and Zq.dtype == torch.float32 and Zq.is_contiguous()
+    else:
+        assert Qhi is not None and Qhi.shape == (Mq, D) and Qhi.is_contiguous() and Qhi.dtype == Bhi.dtype
+    sym = colkey is not None
+    if sym:
+        assert colkey.shape == (nb_img, Mq) and colkey.dtype == torch.int64 and colkey.is_contiguous()
+    if q_self is not None:
+        assert q_self.dtype == torch.int32
+    out = torch.empty(nb_img, Mq, dtype=torch.float32, device=Bhi.device)
+    rc = lib.ac_refine_min_dist(_ptr(Zq), _ptr(Qhi), _ptr(Qlo), Mq, _ptr(Bhi), _ptr(Blo), _TORCH_TO_AC[Bhi.dtype], nb_img, P, D,
+                                _ptr(rowarg), _ptr(colkey), int(sym), int(q_img0), _ptr(q_self), int(Pq or P), _ptr(out), _stream())
+    check(rc, "ac_refine_min_dist")
+    return out
+
+
 def reduce_weights_sym(rowmin: torch.Tensor, colfull: torch.Tensor, Pq: int, q_img0: int) -> torch.Tensor:
     lib = _lib.load()
     _need_cuda(rowmin, colfull)

@@ -35,17 +35,24 @@ def _mark(tag: str) -> None:
         PROFILE.append((tag, ev))
 
 
+# taus below this go to the refined mode under precision="auto" (one fp16 pass keeps alpha inside
+# 1e-3 with a 2x margin from tau = 1 on, also at real-data patch norms; tau = 0 is the arg-max and needs exact w too)
+AUTO_REFINE_BELOW_TAU = 1.0
+
+
 def resolve_precision(precision: str, taus: Sequence[float]) -> str:
-    """'auto' -> the cheapest mode that keeps alpha inside the 1e-3 max-abs tolerance, from the measured table
-    in DESIGN.md section 5 (config-2 scale): one fp16 pass for tau >= 0.5 (and for tau = 0, the arg-max),
-    split-fp16 (3 passes) for 0 < tau < 0.5."""
+    """'auto' -> the cheapest mode that keeps alpha inside the 1e-3 max-abs tolerance with a 2x margin (measured table in
+    DESIGN.md section 5): one fp16 tensor-core pass when every tau >= 1; otherwise 'f16r' = the same pass recording the
+    arg-min + an exact fp32 re-evaluation of the selected pairs (ac_refine_min_dist, ~1.4x the one-pass cost)."""
     if precision != "auto":
         return precision
-    small = [t for t in taus if 0.0 < abs(float(t)) < 0.5]
-    return "f16x3" if small else "f16"
+    small = [t for t in taus if abs(float(t)) < AUTO_REFINE_BELOW_TAU]
+    return "f16r" if small else "f16"
 
 
-_OPERAND_OF = {"f16": ("f16", False), "bf16": ("bf16", False), "f16x3": ("f16", True), "bf16x3": ("bf16", True), "f32": (None, False)}
+_OPERAND_OF = {"f16": ("f16", False), "bf16": ("bf16", False), "f16x3": ("f16", True), "bf16x3": ("bf16", True), "f32": (None, False),
+               "f16r": ("f16", False), "bf16r": ("bf16", False)}
+REFINED = ("f16r", "bf16r")
 
 
 @dataclass
@@ -140,18 +147,37 @@ def min_distance_weights(
 ):
     """Stage 2: w [Nq, P].  mode 'unsupervised' = mean over bank images != self (utils.py:222-227),
     'supervised' = min over bank images (utils.py:230-237).  q_self[i] = bank index of query image i."""
+    refined = precision in REFINED
     if (mode == "unsupervised" and SYMMETRIC and q is bank and precision != "f32" and q.P >= 32 and not return_dmin
             and q_self is None):
         _mark("mindist_begin")
-        rowmin, colmin = ops.min_dist_sym(q.hi, q.lo, q.n2, 0, q.hi, q.lo, q.n2, q.n_img, q.P, precision)
+        if refined:
+            rowmin, rowarg, colkey = ops.min_dist_sym_arg(q.hi, q.lo, q.n2, 0, q.hi, q.lo, q.n2, q.n_img, q.P, precision)
+        else:
+            rowmin, colmin = ops.min_dist_sym(q.hi, q.lo, q.n2, 0, q.hi, q.lo, q.n2, q.n_img, q.P, precision)
         _mark("mindist_end")
-        return ops.reduce_weights_sym(rowmin, colmin, q.P, 0).reshape(q.n_img, q.P)
+        if not refined:
+            return ops.reduce_weights_sym(rowmin, colmin, q.P, 0).reshape(q.n_img, q.P)
+        _mark("refine_begin")
+        dex = ops.refine_min_dist(q.Z, q.hi, q.lo, q.hi, q.lo, q.n_img, q.P, rowarg, colkey=colkey, q_img0=0)
+        _mark("refine_end")
+        own = torch.arange(q.n_img, dtype=torch.int32, device=dex.device)
+        return ops.reduce_weights(dex, q.P, own, "mean").reshape(q.n_img, q.P)
     _mark("mindist_begin")
     if precision == "f32":
         dmin = ops.min_dist(q.Z, None, None, bank.Z, None, None, bank.n_img, bank.P, "f32")
+    elif refined:
+        dmin, arg = ops.min_dist_arg(q.hi, q.lo, q.n2, bank.hi, bank.lo, bank.n2, bank.n_img, bank.P, precision)
     else:
         dmin = ops.min_dist(q.hi, q.lo, q.n2, bank.hi, bank.lo, bank.n2, bank.n_img, bank.P, precision)
     _mark("mindist_end")
+    if refined:
+        if mode == "unsupervised" and q_self is None:
+            q_self = torch.arange(q.n_img, dtype=torch.int32, device=dmin.device)
+        _mark("refine_begin")
+        dmin = ops.refine_min_dist(q.Z, q.hi, q.lo, bank.hi, bank.lo, bank.n_img, bank.P, arg,
+                                   q_self=q_self if mode == "unsupervised" else None, Pq=q.P)
+        _mark("refine_end")
     if mode == "unsupervised":
         if q_self is None:
             q_self = torch.arange(q.n_img, dtype=torch.int32, device=dmin.device)

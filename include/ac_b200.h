@@ -155,6 +155,34 @@ int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn2, int64_t 
 int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
                           float* w, ac_stream_t stream);
 
+/* ---- stage 2, precision mode "f16r": tensor-core search + exact re-evaluation -----------------------
+ * The tensor-core distance carries the fp32 accumulation error of K = D products of magnitude |q||b| (about 3e-3
+ * absolute at D = 4096, |x| ~ 31), too much for softmax(w / tau) once tau < 1 (utils.py:253), while the ARG-min
+ * is far more robust than the value.  The *_arg variants additionally record which bank row won:
+ *   argmin[j*Mq + r]  (ac_min_dist_arg)      row inside bank image j nearest to query row r
+ *   rowarg[j*Mq + r]  (ac_min_dist_sym_arg)  same, for the pairs the query image owns
+ *   colkey[(i-q_img0)*nb_img*P + j*P + c]    (fp32 bits of min d2 << 32) | row inside query image i that is nearest
+ *                                            to bank patch (j,c)  -- the 64-bit counterpart of colmin_d2
+ * (sharded runs exchange colkey column blocks exactly like colmin_d2), and ac_refine_min_dist recomputes
+ *   dmin[j*Mq + r] = || q_r - b_(j, arg) ||_2 = sqrt(sum_k (q_r[k] - b[k])^2)
+ * in fp32 without the |x|^2+|y|^2-2xy cancellation: the query row from Zq (fp32, if not NULL) else from its
+ * operand copy Qhi (+ Qlo), the bank row from the operand copy Bhi (+ Blo).  sym = 1: query image i = q_img0 + r/P,
+ * arg from rowarg where i owns the pair {i,j} else from the low half of colkey[j*Mq + r] (layout [bank image, query row],
+ * i.e. after the column-block exchange); the own image gets 0.  sym = 0: arg from rowarg everywhere; q_self
+ * ([ceil(Mq/Pq)] bank index of each query image, or NULL) names pairs to skip.  Feed dmin to ac_reduce_weights.
+ * Costs one gathered 2*D-byte row per (query row, bank image): ~1/3 of the one-pass GEMM time at config 2.
+ * Needs D % 8 == 0 and D <= 12800, else AC_ERR_UNSUPPORTED (use the X3 modes). */
+int ac_min_dist_arg(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
+                    const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int32_t* argmin, void* ws,
+                    size_t ws_bytes, ac_stream_t stream);
+int ac_min_dist_sym_arg(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                        const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                        int bank_count, int init_colkey, float* rowmin_d2, int32_t* rowarg, uint64_t* colkey, void* ws,
+                        size_t ws_bytes, ac_stream_t stream);
+int ac_refine_min_dist(const float* Zq, const void* Qhi, const void* Qlo, int64_t Mq, const void* Bhi, const void* Blo,
+                       int op_dtype, int nb_img, int P, int D, const int32_t* rowarg, const uint64_t* colkey, int sym,
+                       int q_img0, const int32_t* q_self, int Pq, float* dmin, ac_stream_t stream);
+
 /* ---- stage 3 -----------------------------------------------------------------------------------
  * alpha[t, i, :] = softmax_p(w[i, :] / tau_t) in float64, max-subtracted (identical to
  * Matrix_Alpha_* wherever the reference's exp does not overflow, utils.py:246-255); |tau| < 1e-9

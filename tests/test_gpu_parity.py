@@ -271,6 +271,91 @@ def test_mindist_symmetric_bank_windows_accumulate():
                 assert torch.equal(one[0][j, r], two[0][j, r])
 
 
+# ------------------------------------------------------------------------------- refined mode (arg-min + exact re-evaluation)
+@pytest.mark.parametrize("shape", [(3, 784, 256), (4, 100, 320), (5, 260, 128)])
+def test_mindist_arg_and_refine_kernel(shape):
+    """ac_min_dist_arg names the bank row that won (up to near-ties) and ac_refine_min_dist returns the fp32-exact
+    distance of exactly that pair: compared with fp64 on the same operands."""
+    n, P, D = shape
+    gen = torch.Generator().manual_seed(n * 977 + P)
+    Z = (torch.randn(1, P, D, generator=gen) + 0.5 * torch.randn(n, P, D, generator=gen)).cuda()
+    ps = pipeline.patchset_from_Z(Z, "f16r")
+    assert ps.lo is None
+    dmin, arg = ops.min_dist_arg(ps.hi, None, ps.n2, ps.hi, None, ps.n2, n, P, "f16r")
+    assert arg.dtype == torch.int32 and int(arg.min()) >= 0 and int(arg.max()) < P
+    op = ps.hi.double().cpu().reshape(n, P, D)
+    q = op.reshape(n * P, D)
+    a = arg.cpu().long()
+    for j in range(n):
+        d_all = torch.cdist(q, op[j])                                  # [n*P, P] fp64
+        d_sel = d_all.gather(1, a[j][:, None])[:, 0]
+        d_min = d_all.min(dim=1)[0]
+        other = torch.ones(n * P, dtype=torch.bool)
+        other[j * P:(j + 1) * P] = False                               # own image: distance 0 to itself, any tie is fine
+        assert ((d_sel - d_min)[other] <= 2e-3 * d_min[other] + 1e-6).all()   # the selected row IS the nearest (near-ties aside)
+        # refined value from the operand rows (query side = the operand as well here): exact distance of the selected pair
+    dex = ops.refine_min_dist(None, ps.hi, None, ps.hi, None, n, P, arg).double().cpu()
+    dz = ops.refine_min_dist(Z.reshape(n * P, D).contiguous(), None, None, ps.hi, None, n, P, arg).double().cpu()
+    zq = Z.double().cpu().reshape(n * P, D)
+    for j in range(n):
+        sel = op[j][a[j]]                                              # [n*P, D] selected bank rows
+        want = (q - sel).norm(dim=1)
+        assert ((dex[j] - want).abs() <= 2e-6 * want + 1e-6).all()     # fp32 sum of squares, no cancellation
+        wantz = (zq - sel).norm(dim=1)
+        assert ((dz[j] - wantz).abs() <= 2e-6 * wantz + 1e-6).all()    # query row taken from fp32 Z
+
+
+@pytest.mark.parametrize("n,P,D", [(7, 100, 256), (6, 784, 512), (5, 260, 320)])
+def test_refined_symmetric_equals_refined_all_pairs_and_fp64(n, P, D):
+    """'f16r' through the symmetric kernel (row arg-mins + (distance, row) column keys) and through the all-pairs kernel
+    give the same w; both agree with the fp64 weights of the operands to fp32 round-off (not 5e-4 like one pass)."""
+    gen = torch.Generator().manual_seed(n * 131 + P)
+    Z = (torch.randn(1, P, D, generator=gen) + 0.5 * torch.randn(n, P, D, generator=gen)).cuda()
+    ps = pipeline.patchset_from_Z(Z, "f16r")
+    ps.Z = None                                                        # refine from the operand on both sides
+    try:
+        pipeline.SYMMETRIC = False
+        w_full = pipeline.min_distance_weights(ps, ps, "unsupervised", "f16r")
+        pipeline.SYMMETRIC = True
+        w_sym = pipeline.min_distance_weights(ps, ps, "unsupervised", "f16r")
+    finally:
+        pipeline.SYMMETRIC = True
+    op = ps.hi.double().cpu().reshape(n, P, D)
+    want = torch.empty(n, P, dtype=torch.float64)
+    for i in range(n):
+        want[i] = torch.stack([torch.cdist(op[i], op[j]).min(dim=1)[0] for j in range(n) if j != i], 1).mean(1)
+    assert ((w_sym.double().cpu() - want).abs() / want).max().item() <= 2e-5
+    assert ((w_full.double().cpu() - want).abs() / want).max().item() <= 2e-5
+    assert ((w_sym - w_full).abs() / w_full).max().item() <= 2e-5
+
+
+def test_refined_sharded_slices_and_windows():
+    """Two query slices of one bank in 'f16r' (what two ranks compute: windows accumulate, key column blocks are
+    exchanged, every slice refines its own rows against the whole bank) reproduce the single-slice result bit for bit."""
+    from anomaly_clustering_b200 import distributed
+
+    n, P, D = 7, 96, 128
+    gen = torch.Generator().manual_seed(5)
+    Z = (torch.randn(1, P, D, generator=gen) + 0.5 * torch.randn(n, P, D, generator=gen)).cuda()
+    ps = pipeline.patchset_from_Z(Z, "f16r")
+    w_one = pipeline.min_distance_weights(ps, ps, "unsupervised", "f16r")
+    bounds = distributed.shard_bounds(n, 2)
+    parts = []
+    for a, b in bounds:
+        sl = slice(a * P, b * P)
+        out = ops.min_dist_sym_arg(ps.hi[sl], None, ps.n2[sl], a, ps.hi, None, ps.n2, n, P, "f16r", bank_window=(a, b - a), init=True)
+        out = ops.min_dist_sym_arg(ps.hi[sl], None, ps.n2[sl], a, ps.hi, None, ps.n2, n, P, "f16r", bank_window=(b % n, n - (b - a)),
+                                   init=False, out=out)
+        parts.append(out)
+    for r, (a, b) in enumerate(bounds):
+        sl = slice(a * P, b * P)
+        colfull = torch.cat([parts[s][2][:, a * P:b * P] for s in range(2)], dim=0).contiguous()
+        dex = ops.refine_min_dist(ps.Z[sl], ps.hi[sl], None, ps.hi, None, n, P, parts[r][1], colkey=colfull, q_img0=a)
+        own = torch.arange(a, b, dtype=torch.int32, device="cuda")
+        w = ops.reduce_weights(dex, P, own, "mean").reshape(b - a, P)
+        assert torch.equal(w, w_one[a:b])
+
+
 # ------------------------------------------------------------------------------- stage 3
 def test_alpha_golden(golden_dir):
     g = gload(golden_dir, "alpha_small")
