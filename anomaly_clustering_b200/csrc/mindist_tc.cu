@@ -67,6 +67,10 @@ struct __align__(64) TcParams {
   int dynamic;               // 1: units are claimed from a global counter (work stealing) instead of round-robin
   unsigned long long* counter;
   // arg-min tracking (kArg kernels; the exact re-evaluation of ac_refine_min_dist needs WHICH bank row won)
+  // per-category banks in one launch (the reference runs one make_category_data per category, examples/main.py:353):
+  // groups[2*j], groups[2*j+1] = first image and image count of the category of bank image j; pairs exist only inside
+  // a category and ownership is the circular rule inside it.  null = one category (all images).
+  const int* groups;
   int* rowarg;                   // [nb_img, Mq] row inside bank image j that is nearest to query row r
   unsigned long long* colkey;    // sym: [nq_img, nb_img*P] (fp32 bits of d2 << 32) | row inside the query image, atomicMin target
 };
@@ -80,6 +84,18 @@ __host__ __device__ inline bool pair_owned(int i, int j, int N) {
   if (2 * d < N) return true;
   if (2 * d == N) return i < j;
   return false;
+}
+
+// ownership with categories: image i owns the pair {i, j} iff both lie in the category of j and i owns it there
+__host__ __device__ inline bool pair_owned_grouped(const int* groups, int i, int j, int N) {
+  if (!groups) return pair_owned(i, j, N);
+#ifdef __CUDA_ARCH__
+  const int g0 = __ldg(groups + 2 * j), gn = __ldg(groups + 2 * j + 1);
+#else
+  const int g0 = groups[2 * j], gn = groups[2 * j + 1];
+#endif
+  if (i < g0 || i >= g0 + gn) return false;
+  return pair_owned(i - g0, j - g0, gn);
 }
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -522,7 +538,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
       const bool rvalid = row < p.Mq;
       // sym mode: this row contributes (row-min and column-min) only if its image owns the pair
       const int irow = p.q_img0 + (int)((rvalid ? row : p.Mq - 1) / p.P);
-      const bool act = rvalid && (!p.sym || pair_owned(irow, img, p.nb_img));
+      const bool act = rvalid && (!p.sym || pair_owned_grouped(p.groups, irow, img, p.nb_img));
       const float qn = rvalid ? __ldg(p.qn2 + row) : 0.f;
       // images covered by this warp's 32 consecutive rows (at most two when P >= 32)
       const long long wrow0 = row - lane;
@@ -668,7 +684,7 @@ __device__ __forceinline__ bool unit_has_work(const TcParams& p, int G, int mb, 
   const long long r0 = (long long)mb * rows_per_mb, r1 = min(p.Mq, r0 + rows_per_mb) - 1;
   const int i0 = p.q_img0 + (int)(r0 / p.P), i1 = p.q_img0 + (int)(r1 / p.P);
   for (int i = i0; i <= i1; ++i)
-    if (pair_owned(i, img, p.nb_img)) return true;
+    if (pair_owned_grouped(p.groups, i, img, p.nb_img)) return true;
   return false;
 }
 
@@ -682,6 +698,8 @@ __global__ void __launch_bounds__(1024) build_units_kernel(TcParams p, int G, in
   const int n_groups = (p.n_mblocks + p.GM - 1) / p.GM;
   const long long rows = (long long)n_groups * p.KU;
   const long long rows_per_mb = (long long)kTileM * G;
+  // raster row = (group of GM query blocks, candidate bank image); the candidates of a group are walked circularly
+  // from the first image after the group's first query image (ownership looks forward in that order)
   auto row_info = [&](long long r, int& mg, int& img, int& gm_cur) {
     mg = (int)(r / p.KU);
     const int k = (int)(r - (long long)mg * p.KU);
@@ -689,6 +707,7 @@ __global__ void __launch_bounds__(1024) build_units_kernel(TcParams p, int G, in
     const int ig = p.q_img0 + (int)(((long long)mg * p.GM * rows_per_mb) / p.P);
     img = (ig + 1 + k) % p.nb_img;
   };
+  (void)rows_per_mb;
   // contiguous slice of rows per thread keeps the raster order after the scan
   const long long per = (rows + blockDim.x - 1) / blockDim.x;
   const long long ra = min(rows, (long long)tid * per), rb = min(rows, ra + per);
@@ -797,7 +816,8 @@ static int launch_tc(const TcParams& prm, int num_sms, cudaStream_t st) {
 int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long long Mq, const void* Bhi, const void* Blo,
                       const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int* err_flag, cudaStream_t st,
                       int sym = 0, int q_img0 = 0, unsigned int* colmin = nullptr, void* unit_ws = nullptr, size_t unit_ws_bytes = 0,
-                      int win_begin = 0, int win_count = -1, int* rowarg = nullptr, unsigned long long* colkey = nullptr) {
+                      int win_begin = 0, int win_count = -1, int* rowarg = nullptr, unsigned long long* colkey = nullptr,
+                      const int* groups = nullptr) {
   const bool bf16 = (precision == AC_PREC_BF16 || precision == AC_PREC_BF16X3);
   const bool x3 = (precision == AC_PREC_F16X3 || precision == AC_PREC_BF16X3);
   if (D % 8 != 0) return AC_ERR_UNSUPPORTED;  // TMA needs a 16-byte row pitch
@@ -821,18 +841,21 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.dynamic = g_tc_dynamic;
   prm.counter = (unsigned long long*)((char*)err_flag + 128);   // inside the zeroed 256-byte workspace header
   prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin; prm.units = nullptr;
-  prm.rowarg = rowarg; prm.colkey = colkey;
+  prm.rowarg = rowarg; prm.colkey = colkey; prm.groups = groups;
   const bool arg = (rowarg != nullptr);
   if (arg && sym && !colkey) return AC_ERR_INVALID;
   prm.win_begin = win_begin; prm.win_count = (win_count < 0) ? nb_img : win_count;
-  // bank images a raster group of GM query blocks can own: N/2 after each of the images it spans
-  prm.KU = std::min(nb_img, nb_img / 2 + (int)(((long long)prm.GM * kTileM * G - 1) / P) + 1);
+  // bank images a raster group of GM query blocks can own: N/2 after each of the images it spans (with categories the
+  // group may end in the middle of one whose images wrap around: every bank image is a candidate)
+  prm.KU = groups ? nb_img : std::min(nb_img, nb_img / 2 + (int)(((long long)prm.GM * kTileM * G - 1) / P) + 1);
   prm.total_units = (long long)prm.n_mblocks * nb_img;
   if (sym) {
     // raster order: groups of GM query blocks; inside a group walk the bank images the group owns and,
     // per bank image, every block of the group that owns the pair (blocks sharing a bank image run
     // together).  Built on the device (build_units_kernel).
-    const long long max_units = (long long)prm.n_mblocks * prm.KU;
+    // a query block spans at most rows/P + 2 images, each owns at most half of its category (<= nb_img / 2 + 1 images)
+    const long long span = ((long long)kTileM * G + P - 1) / P + 1;
+    const long long max_units = (long long)prm.n_mblocks * std::min<long long>(nb_img, span * (nb_img / 2 + 1));
     if (!unit_ws || unit_ws_bytes < 16 + (size_t)max_units * sizeof(int2)) return AC_ERR_WORKSPACE;
     long long* d_n = (long long*)unit_ws;
     int2* d_units = (int2*)((char*)unit_ws + 16);
@@ -883,15 +906,16 @@ extern "C" int ac_debug_set(int key, int value) {
 }
 
 __global__ void reduce_weights_sym_kernel(const float* __restrict__ rowmin, const float* __restrict__ colmin, long long Mq, int nb_img,
-                                          int Pq, int q_img0, float* __restrict__ w) {
+                                          int Pq, int q_img0, const int* __restrict__ groups, float* __restrict__ w) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (r >= Mq) return;
   const int i = q_img0 + (int)(r / Pq);
   float s = 0.f;
   int cnt = 0;
-  for (int j = 0; j < nb_img; ++j) {
+  const int j0 = groups ? groups[2 * i] : 0, j1 = groups ? j0 + groups[2 * i + 1] : nb_img;   // the image's own category
+  for (int j = j0; j < j1; ++j) {
     if (j == i) continue;
-    const float d2 = pair_owned(i, j, nb_img) ? __ldg(rowmin + (long long)j * Mq + r) : __ldg(colmin + (long long)j * Mq + r);
+    const float d2 = pair_owned_grouped(groups, i, j, nb_img) ? __ldg(rowmin + (long long)j * Mq + r) : __ldg(colmin + (long long)j * Mq + r);
     s += sqrtf(d2);   // same left-to-right order as the reference's torch.mean over the cat'ed columns
     ++cnt;
   }
@@ -901,7 +925,7 @@ __global__ void reduce_weights_sym_kernel(const float* __restrict__ rowmin, cons
 static int min_dist_sym_impl(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
                              const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
                              int bank_count, int init_colmin, float* rowmin_d2, float* colmin_d2, int32_t* rowarg, uint64_t* colkey,
-                             void* ws, size_t ws_bytes, ac_stream_t stream) {
+                             const int32_t* groups, void* ws, size_t ws_bytes, ac_stream_t stream) {
   const bool arg = (rowarg != nullptr);
   if (!Qhi || !Bhi || !Qn2 || !Bn2 || !rowmin_d2 || (!arg && !colmin_d2) || (arg && !colkey) || Mq < 0 || nb_img < 1 || P < 1 ||
       D < 1 || q_img0 < 0)
@@ -925,7 +949,7 @@ static int min_dist_sym_impl(const void* Qhi, const void* Qlo, const float* Qn2,
   }
   return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, rowmin_d2, (int*)ws, st, 1, q_img0,
                            (unsigned int*)colmin_d2, (char*)ws + 256, ws_bytes - 256, bank_begin, bank_count, rowarg,
-                           (unsigned long long*)colkey);
+                           (unsigned long long*)colkey, groups);
 }
 
 extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
@@ -933,7 +957,16 @@ extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn
                                int bank_count, int init_colmin, float* rowmin_d2, float* colmin_d2, void* ws, size_t ws_bytes,
                                ac_stream_t stream) {
   return min_dist_sym_impl(Qhi, Qlo, Qn2, Mq, q_img0, Bhi, Blo, Bn2, nb_img, P, D, precision, bank_begin, bank_count, init_colmin,
-                           rowmin_d2, colmin_d2, nullptr, nullptr, ws, ws_bytes, stream);
+                           rowmin_d2, colmin_d2, nullptr, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int ac_min_dist_sym_ex(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                                  const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                                  int bank_count, int init, float* rowmin_d2, float* colmin_d2, int32_t* rowarg, uint64_t* colkey,
+                                  const int32_t* groups, void* ws, size_t ws_bytes, ac_stream_t stream) {
+  if ((rowarg != nullptr) != (colkey != nullptr)) return AC_ERR_INVALID;
+  return min_dist_sym_impl(Qhi, Qlo, Qn2, Mq, q_img0, Bhi, Blo, Bn2, nb_img, P, D, precision, bank_begin, bank_count, init,
+                           rowmin_d2, colmin_d2, rowarg, colkey, groups, ws, ws_bytes, stream);
 }
 
 extern "C" int ac_min_dist_sym_arg(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
@@ -942,25 +975,33 @@ extern "C" int ac_min_dist_sym_arg(const void* Qhi, const void* Qlo, const float
                                    size_t ws_bytes, ac_stream_t stream) {
   if (!rowarg || !colkey) return AC_ERR_INVALID;
   return min_dist_sym_impl(Qhi, Qlo, Qn2, Mq, q_img0, Bhi, Blo, Bn2, nb_img, P, D, precision, bank_begin, bank_count, init_colkey,
-                           rowmin_d2, nullptr, rowarg, colkey, ws, ws_bytes, stream);
+                           rowmin_d2, nullptr, rowarg, colkey, nullptr, ws, ws_bytes, stream);
 }
 
-extern "C" int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
-                                     float* w, ac_stream_t stream) {
+extern "C" int ac_reduce_weights_sym_ex(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
+                                        const int32_t* groups, float* w, ac_stream_t stream) {
   if (!rowmin_d2 || !colmin_d2 || !w || Mq < 0 || nb_img < 1 || Pq < 1 || q_img0 < 0) return AC_ERR_INVALID;
   int rc = check_device();
   if (rc) return rc;
   if (Mq == 0) return AC_OK;
-  reduce_weights_sym_kernel<<<(unsigned)((Mq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowmin_d2, colmin_d2, Mq, nb_img, Pq, q_img0, w);
+  reduce_weights_sym_kernel<<<(unsigned)((Mq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowmin_d2, colmin_d2, Mq, nb_img, Pq, q_img0,
+                                                                                            groups, w);
   AC_LAUNCH_CHECK();
   return AC_OK;
+}
+
+extern "C" int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
+                                     float* w, ac_stream_t stream) {
+  return ac_reduce_weights_sym_ex(rowmin_d2, colmin_d2, Mq, nb_img, Pq, q_img0, nullptr, w, stream);
 }
 
 extern "C" size_t ac_min_dist_workspace_bytes(int64_t Mq, int nb_img, int P, int D, int precision) {
   (void)D; (void)precision;
   // 256 B pipeline-watchdog flag + (symmetric form) the raster list of (query block, bank image) units
+  // sized for the smaller block (128 rows, single-CTA MMAs): more blocks, same per-block bound as launch_mindist_tc
   const long long mblocks = (Mq + 127) / 128;
-  const long long per_mb = std::min<long long>(nb_img, nb_img / 2 + 64 * 256 / std::max(1, P) + 2);
+  const long long span = (256 + std::max(1, P) - 1) / std::max(1, P) + 1;
+  const long long per_mb = std::min<long long>(nb_img, span * (nb_img / 2 + 1));
   return 256 + 16 + (size_t)(mblocks * per_mb) * sizeof(int2);
 }
 

@@ -40,6 +40,7 @@ struct RefineParams {
   const unsigned long long* colkey;   // [nb_img, Mq] (sym) or null
   int sym, q_img0;
   const int* q_self;                  // non-sym: bank index of each query image (its pair is skipped) or null
+  const int* groups;                  // sym: (first image, count) of the category of every bank image, or null
   float* dex;                         // [nb_img, Mq]
   int Jb;
 };
@@ -97,7 +98,11 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineParams 
   const float4* qlo4 = s_q + (rr * 2 + 0) * G8;
   const float4* qhi4 = s_q + (rr * 2 + 1) * G8;
   const int j0 = blockIdx.y * p.Jb, j1 = min(p.nb_img, j0 + p.Jb);
+  // categories: only the images of the query image's own category are its bank (the rest is never read by the reduction)
+  int g0 = 0, gn = p.nb_img;
+  if (p.sym && p.groups) { g0 = __ldg(p.groups + 2 * i); gn = __ldg(p.groups + 2 * i + 1); }
   for (int j = j0 + par; j < j1; j += 2) {
+    if (j < g0 || j >= g0 + gn) continue;
     if (j == i) {
       if (lane == 0) p.dex[(long long)j * p.Mq + r] = 0.f;     // own image: excluded by the reduction
       continue;
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineParams 
     int c = 0;
     if (lane == 0) {
       const long long e = (long long)j * p.Mq + r;
-      if (p.sym && !pair_owned_r(i, j, p.nb_img)) c = (int)(unsigned int)(__ldg(p.colkey + e) & 0xffffffffull);
+      if (p.sym && !pair_owned_r(i - g0, j - g0, gn)) c = (int)(unsigned int)(__ldg(p.colkey + e) & 0xffffffffull);
       else c = __ldg(p.rowarg + e);
       c = min(max(c, 0), p.P - 1);
     }
@@ -152,7 +157,7 @@ extern "C" int ac_debug_set_refine(int mb) {
 
 extern "C" int ac_refine_min_dist(const float* Zq, const void* Qhi, const void* Qlo, int64_t Mq, const void* Bhi, const void* Blo,
                                   int op_dtype, int nb_img, int P, int D, const int32_t* rowarg, const uint64_t* colkey, int sym,
-                                  int q_img0, const int32_t* q_self, int Pq, float* dmin, ac_stream_t stream) {
+                                  int q_img0, const int32_t* q_self, int Pq, const int32_t* groups, float* dmin, ac_stream_t stream) {
   if ((!Zq && !Qhi) || !Bhi || !rowarg || !dmin || Mq < 0 || nb_img < 1 || P < 1 || D < 1 || Pq < 1 || q_img0 < 0) return AC_ERR_INVALID;
   if (op_dtype != AC_DT_F16 && op_dtype != AC_DT_BF16) return AC_ERR_INVALID;
   if (sym && (!colkey || Pq != P)) return AC_ERR_INVALID;
@@ -166,15 +171,16 @@ extern "C" int ac_refine_min_dist(const float* Zq, const void* Qhi, const void* 
   p.Zq = Zq; p.Qhi = Qhi; p.Qlo = Qlo; p.Bhi = Bhi; p.Blo = Blo;
   p.Mq = Mq; p.nb_img = nb_img; p.P = P; p.D = D; p.Pq = Pq;
   p.rowarg = rowarg; p.colkey = (const unsigned long long*)colkey; p.sym = sym; p.q_img0 = q_img0; p.q_self = q_self; p.dex = dmin;
+  p.groups = sym ? groups : nullptr;
   // bank images per group: their operand rows (64 MB by default) stay L2-resident while every query chunk passes
   const double img_bytes = (double)P * D * 2.0 * (Blo ? 2 : 1);
   p.Jb = (int)std::max(2.0, std::min(64.0, g_refine_l2_mb * 1.0e6 / img_bytes));
   p.Jb &= ~1;                                                      // the two warps of a row take alternate images
   const long long chunks = (Mq + kRQ - 1) / kRQ;
-  const int groups = (nb_img + p.Jb - 1) / p.Jb;
-  if (chunks > 0x7fffffffLL || groups > 65535) return AC_ERR_UNSUPPORTED;
+  const int nbg = (nb_img + p.Jb - 1) / p.Jb;
+  if (chunks > 0x7fffffffLL || nbg > 65535) return AC_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)chunks, (unsigned)groups);
+  dim3 grid((unsigned)chunks, (unsigned)nbg);
   if (op_dtype == AC_DT_F16) {
     AC_CUDA(cudaFuncSetAttribute(refine_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     refine_kernel<__half><<<grid, kRefThreads, smem, st>>>(p);

@@ -27,14 +27,18 @@ int check_device() {
 
 // one thread per query row; dmin is [nb_img, Mq] so consecutive threads read consecutive addresses
 __global__ void __launch_bounds__(256) reduce_weights_kernel(const float* __restrict__ dmin, long long Mq, int nb_img, int Pq,
-                                                             const int* __restrict__ q_self, int mode, float* __restrict__ w) {
+                                                             const int* __restrict__ q_self, const int* __restrict__ groups, int mode,
+                                                             float* __restrict__ w) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (r >= Mq) return;
   const int self = q_self ? q_self[r / Pq] : -1;
+  // categories (groups != null, needs q_self): the bank of a query image is its own category only
+  int j0 = 0, j1 = nb_img;
+  if (groups && self >= 0) { j0 = groups[2 * self]; j1 = j0 + groups[2 * self + 1]; }
   if (mode == AC_REDUCE_MEAN) {
     float s = 0.f;
     int cnt = 0;
-    for (int j = 0; j < nb_img; ++j) {
+    for (int j = j0; j < j1; ++j) {
       if (j == self) continue;
       s += __ldg(dmin + (long long)j * Mq + r);  // same left-to-right order as torch.mean over the cat'ed columns
       ++cnt;
@@ -42,7 +46,7 @@ __global__ void __launch_bounds__(256) reduce_weights_kernel(const float* __rest
     w[r] = cnt > 0 ? s / (float)cnt : nanf("");
   } else {
     float m = INFINITY;
-    for (int j = 0; j < nb_img; ++j) {
+    for (int j = j0; j < j1; ++j) {
       if (j == self) continue;
       m = fminf(m, __ldg(dmin + (long long)j * Mq + r));
     }
@@ -246,16 +250,22 @@ extern "C" int ac_device_ok(int dev) {
   return major == 10 ? AC_OK : AC_ERR_DEVICE;
 }
 
-extern "C" int ac_reduce_weights(const float* dmin, int64_t Mq, int nb_img, int Pq, const int32_t* q_self, int mode, float* w,
-                                 ac_stream_t stream) {
+extern "C" int ac_reduce_weights_ex(const float* dmin, int64_t Mq, int nb_img, int Pq, const int32_t* q_self, const int32_t* groups,
+                                    int mode, float* w, ac_stream_t stream) {
   if (!dmin || !w || Mq < 0 || nb_img < 1 || Pq < 1) return AC_ERR_INVALID;
   if (mode != AC_REDUCE_MEAN && mode != AC_REDUCE_MIN) return AC_ERR_INVALID;
+  if (groups && !q_self) return AC_ERR_INVALID;
   int rc = check_device();
   if (rc) return rc;
   if (Mq == 0) return AC_OK;
-  reduce_weights_kernel<<<(unsigned)((Mq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dmin, Mq, nb_img, Pq, q_self, mode, w);
+  reduce_weights_kernel<<<(unsigned)((Mq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dmin, Mq, nb_img, Pq, q_self, groups, mode, w);
   AC_LAUNCH_CHECK();
   return AC_OK;
+}
+
+extern "C" int ac_reduce_weights(const float* dmin, int64_t Mq, int nb_img, int Pq, const int32_t* q_self, int mode, float* w,
+                                 ac_stream_t stream) {
+  return ac_reduce_weights_ex(dmin, Mq, nb_img, Pq, q_self, nullptr, mode, w, stream);
 }
 
 extern "C" int ac_alpha(const float* w, int N, int P, const double* taus_host, int T, double* alpha64, float* alpha32,

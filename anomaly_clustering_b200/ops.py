@@ -60,6 +60,31 @@ def patch_grid(H: int, W: int, patchsize: int, stride: int) -> Tuple[int, int]:
     return ((H + 2 * pad - (patchsize - 1) - 1) // stride + 1, (W + 2 * pad - (patchsize - 1) - 1) // stride + 1)
 
 
+def make_groups(sizes: Sequence[int], device) -> torch.Tensor:
+    """Category table of the _ex entry points: int32 [sum(sizes), 2] = (first image, image count) of the category of every
+    image, for categories stored back to back (per-category banks, examples/main.py:353)."""
+    key = (tuple(int(n) for n in sizes), str(torch.device(device)))
+    t = _GROUPS_CACHE.get(key)
+    if t is None:                          # built once per layout: no host-to-device copy inside a step
+        rows, start = [], 0
+        for n in key[0]:
+            rows += [[start, n]] * n
+            start += n
+        t = torch.tensor(rows, dtype=torch.int32).reshape(-1, 2).contiguous().to(device)
+        if len(_GROUPS_CACHE) > 64:
+            _GROUPS_CACHE.clear()
+        _GROUPS_CACHE[key] = t
+    return t
+
+
+_GROUPS_CACHE = {}
+
+
+def _groups_ok(groups, nb_img):
+    if groups is not None:
+        assert groups.dtype == torch.int32 and groups.shape == (nb_img, 2) and groups.is_contiguous() and groups.is_cuda
+
+
 def embed(
     features: Sequence[torch.Tensor],
     patchsize: int,
@@ -168,7 +193,7 @@ def min_dist(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, 
 
 
 def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str,
-                 bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None):
+                 bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None, groups: Optional[torch.Tensor] = None):
     """Symmetric self-bank form: (rowmin_d2 [nb_img, Mq], colmin_d2 [Mq/P, nb_img*P]) squared distances.
     bank_window=(begin, count) restricts the launch to a circular range of bank images; pass the previous
     call's result as `out` with init=False to accumulate a second window into the same buffers."""
@@ -185,8 +210,10 @@ def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int,
     begin, count = bank_window if bank_window is not None else (0, nb_img)
     ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
-    rc = lib.ac_min_dist_sym(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
-                             int(begin), int(count), int(bool(init)), _ptr(rowmin), _ptr(colmin), _ptr(ws), ws_bytes, _stream())
+    _groups_ok(groups, nb_img)
+    rc = lib.ac_min_dist_sym_ex(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
+                                int(begin), int(count), int(bool(init)), _ptr(rowmin), _ptr(colmin), None, None, _ptr(groups),
+                                _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_min_dist_sym")
     return rowmin, colmin
 
@@ -209,7 +236,7 @@ def min_dist_arg(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: s
 
 
 def min_dist_sym_arg(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str,
-                     bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None):
+                     bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None, groups: Optional[torch.Tensor] = None):
     """ac_min_dist_sym_arg: (rowmin_d2 [nb_img, Mq], rowarg [nb_img, Mq] int32, colkey [Mq/P, nb_img*P] int64 =
     (fp32 bits of the column minimum << 32) | row inside the query image).  Windows / accumulation as min_dist_sym."""
     lib = _lib.load()
@@ -226,16 +253,17 @@ def min_dist_sym_arg(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: 
     begin, count = bank_window if bank_window is not None else (0, nb_img)
     ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
-    rc = lib.ac_min_dist_sym_arg(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
-                                 int(begin), int(count), int(bool(init)), _ptr(rowmin), _ptr(rowarg), _ptr(colkey), _ptr(ws),
-                                 ws_bytes, _stream())
+    _groups_ok(groups, nb_img)
+    rc = lib.ac_min_dist_sym_ex(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
+                                int(begin), int(count), int(bool(init)), _ptr(rowmin), None, _ptr(rowarg), _ptr(colkey),
+                                _ptr(groups), _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_min_dist_sym_arg")
     return rowmin, rowarg, colkey
 
 
 def refine_min_dist(Zq: Optional[torch.Tensor], Qhi, Qlo, Bhi, Blo, nb_img: int, P: int, rowarg: torch.Tensor,
                     colkey: Optional[torch.Tensor] = None, q_img0: int = 0, q_self: Optional[torch.Tensor] = None,
-                    Pq: Optional[int] = None) -> torch.Tensor:
+                    Pq: Optional[int] = None, groups: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ac_refine_min_dist: exact fp32 distances [nb_img, Mq] of the (query row, selected bank row) pairs.
     colkey given -> symmetric form (layout [nb_img, Mq], i.e. after the column-block exchange)."""
     lib = _lib.load()
@@ -253,32 +281,39 @@ def refine_min_dist(Zq: Optional[torch.Tensor], Qhi, Qlo, Bhi, Blo, nb_img: int,
         assert colkey.shape == (nb_img, Mq) and colkey.dtype == torch.int64 and colkey.is_contiguous()
     if q_self is not None:
         assert q_self.dtype == torch.int32
+    _groups_ok(groups, nb_img)
     out = torch.empty(nb_img, Mq, dtype=torch.float32, device=Bhi.device)
     rc = lib.ac_refine_min_dist(_ptr(Zq), _ptr(Qhi), _ptr(Qlo), Mq, _ptr(Bhi), _ptr(Blo), _TORCH_TO_AC[Bhi.dtype], nb_img, P, D,
-                                _ptr(rowarg), _ptr(colkey), int(sym), int(q_img0), _ptr(q_self), int(Pq or P), _ptr(out), _stream())
+                                _ptr(rowarg), _ptr(colkey), int(sym), int(q_img0), _ptr(q_self), int(Pq or P), _ptr(groups),
+                                _ptr(out), _stream())
     check(rc, "ac_refine_min_dist")
     return out
 
 
-def reduce_weights_sym(rowmin: torch.Tensor, colfull: torch.Tensor, Pq: int, q_img0: int) -> torch.Tensor:
+def reduce_weights_sym(rowmin: torch.Tensor, colfull: torch.Tensor, Pq: int, q_img0: int,
+                       groups: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     _need_cuda(rowmin, colfull)
     nb_img, Mq = rowmin.shape
     assert colfull.shape == rowmin.shape and colfull.is_contiguous() and rowmin.is_contiguous()
+    _groups_ok(groups, nb_img)
     w = torch.empty(Mq, dtype=torch.float32, device=rowmin.device)
-    check(lib.ac_reduce_weights_sym(_ptr(rowmin), _ptr(colfull), Mq, nb_img, Pq, q_img0, _ptr(w), _stream()), "ac_reduce_weights_sym")
+    check(lib.ac_reduce_weights_sym_ex(_ptr(rowmin), _ptr(colfull), Mq, nb_img, Pq, q_img0, _ptr(groups), _ptr(w), _stream()),
+          "ac_reduce_weights_sym")
     return w
 
 
-def reduce_weights(dmin: torch.Tensor, Pq: int, q_self: Optional[torch.Tensor], mode: str) -> torch.Tensor:
+def reduce_weights(dmin: torch.Tensor, Pq: int, q_self: Optional[torch.Tensor], mode: str,
+                   groups: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     _need_cuda(dmin, q_self)
     nb_img, Mq = dmin.shape
+    _groups_ok(groups, nb_img)
     w = torch.empty(Mq, dtype=torch.float32, device=dmin.device)
     m = _lib.AC_REDUCE_MEAN if mode == "mean" else _lib.AC_REDUCE_MIN
     if q_self is not None:
         assert q_self.dtype == torch.int32 and q_self.numel() * Pq >= Mq
-    check(lib.ac_reduce_weights(_ptr(dmin), Mq, nb_img, Pq, _ptr(q_self), m, _ptr(w), _stream()), "ac_reduce_weights")
+    check(lib.ac_reduce_weights_ex(_ptr(dmin), Mq, nb_img, Pq, _ptr(q_self), _ptr(groups), m, _ptr(w), _stream()), "ac_reduce_weights")
     return w
 
 

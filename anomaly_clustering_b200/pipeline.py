@@ -144,25 +144,29 @@ def min_distance_weights(
     precision: str = "f16",
     q_self: Optional[torch.Tensor] = None,
     return_dmin: bool = False,
+    groups: Optional[torch.Tensor] = None,
 ):
     """Stage 2: w [Nq, P].  mode 'unsupervised' = mean over bank images != self (utils.py:222-227),
-    'supervised' = min over bank images (utils.py:230-237).  q_self[i] = bank index of query image i."""
+    'supervised' = min over bank images (utils.py:230-237).  q_self[i] = bank index of query image i.
+    groups (ops.make_groups): the images are several categories back to back, each its own bank (symmetric form only)."""
     refined = precision in REFINED
     if (mode == "unsupervised" and SYMMETRIC and q is bank and precision != "f32" and q.P >= 32 and not return_dmin
             and q_self is None):
         _mark("mindist_begin")
         if refined:
-            rowmin, rowarg, colkey = ops.min_dist_sym_arg(q.hi, q.lo, q.n2, 0, q.hi, q.lo, q.n2, q.n_img, q.P, precision)
+            rowmin, rowarg, colkey = ops.min_dist_sym_arg(q.hi, q.lo, q.n2, 0, q.hi, q.lo, q.n2, q.n_img, q.P, precision, groups=groups)
         else:
-            rowmin, colmin = ops.min_dist_sym(q.hi, q.lo, q.n2, 0, q.hi, q.lo, q.n2, q.n_img, q.P, precision)
+            rowmin, colmin = ops.min_dist_sym(q.hi, q.lo, q.n2, 0, q.hi, q.lo, q.n2, q.n_img, q.P, precision, groups=groups)
         _mark("mindist_end")
         if not refined:
-            return ops.reduce_weights_sym(rowmin, colmin, q.P, 0).reshape(q.n_img, q.P)
+            return ops.reduce_weights_sym(rowmin, colmin, q.P, 0, groups=groups).reshape(q.n_img, q.P)
         _mark("refine_begin")
-        dex = ops.refine_min_dist(q.Z, q.hi, q.lo, q.hi, q.lo, q.n_img, q.P, rowarg, colkey=colkey, q_img0=0)
+        dex = ops.refine_min_dist(q.Z, q.hi, q.lo, q.hi, q.lo, q.n_img, q.P, rowarg, colkey=colkey, q_img0=0, groups=groups)
         _mark("refine_end")
         own = torch.arange(q.n_img, dtype=torch.int32, device=dex.device)
-        return ops.reduce_weights(dex, q.P, own, "mean").reshape(q.n_img, q.P)
+        return ops.reduce_weights(dex, q.P, own, "mean", groups=groups).reshape(q.n_img, q.P)
+    if groups is not None:
+        raise ValueError("per-category groups need the symmetric unsupervised form (P >= 32, tensor-core precision)")
     _mark("mindist_begin")
     if precision == "f32":
         dmin = ops.min_dist(q.Z, None, None, bank.Z, None, None, bank.n_img, bank.P, "f32")
@@ -190,7 +194,7 @@ def min_distance_weights(
     return (w, dmin) if return_dmin else w
 
 
-def alpha_X_dist(ps: PatchSet, w: Optional[torch.Tensor], taus: Sequence[float], features=None, embed_args=None):
+def alpha_X_dist(ps: PatchSet, w: Optional[torch.Tensor], taus: Sequence[float], features=None, embed_args=None, want_dmat=True):
     """Stage 3 for every tau from one w.  w=None -> 'average' mode (main.py:290-291).
     When the PatchSet carries no fp32 Z, X is computed straight from `features` (ac_weighted_embed_from_features)."""
     N, P, D = ps.n_img, ps.P, ps.D
@@ -208,7 +212,7 @@ def alpha_X_dist(ps: PatchSet, w: Optional[torch.Tensor], taus: Sequence[float],
         patchsize, stride, Dp, layernorm = embed_args
         X = torch.stack([ops.weighted_embed_from_features(features, a32[t], patchsize, stride, Dp, D, layernorm=layernorm)
                          for t in range(a32.shape[0])])
-    Dm = torch.stack([ops.pairwise_l2(X[t]) for t in range(a32.shape[0])])
+    Dm = torch.stack([ops.pairwise_l2(X[t]) for t in range(a32.shape[0])]) if want_dmat else None
     return a64, a32, X, Dm
 
 
@@ -272,13 +276,41 @@ def run_categories(
     taus: Sequence[float] = (1.0,),
     precision: str = "auto",
     keep_z: bool = True,
+    layernorm: bool = True,
 ) -> List[PathResult]:
     """Several independent categories (the reference's own semantics: one make_category_data per category, each with
-    its own bank -- examples/main.py:353) from ONE batch of hooked features: `features` hold the images of all
-    categories back to back, `sizes[c]` images each.  Returns one PathResult per category."""
+    its own bank -- examples/main.py:353) from ONE batch of hooked features and ONE launch sequence: `features` hold the
+    images of all categories back to back, `sizes[c]` images each.  The embed, the tensor-core pass (image pairs only
+    inside a category: ac_min_dist_sym_ex with a category table), the reductions, alpha and X run once for all
+    categories; only the small per-category distance matrices are separate launches.  Returns one PathResult per category
+    (views into the shared tensors).  Shapes the batched form does not cover run category by category."""
+    precision = resolve_precision(precision, taus)
+    sizes = [int(n) for n in sizes]
+    views = [ops.feature_view(f) for f in features]
+    N = views[0].shape[0]
+    if sum(sizes) != N:
+        raise ValueError("sizes sum to %d but the features hold %d images" % (sum(sizes), N))
+    h, w_ = ops.patch_grid(views[0].shape[2], views[0].shape[3], patchsize, stride)
+    batched = SYMMETRIC and precision != "f32" and h * w_ >= 32 and min(sizes) >= 2
+    if not batched:
+        out, start = [], 0
+        for n in sizes:
+            out.append(run_path([f[start:start + n] for f in features], patchsize, stride, pretrain_dim, target_dim, "unsupervised",
+                                taus, precision=precision, keep_z=keep_z, layernorm=layernorm))
+            start += n
+        return out
+    if not keep_z and not z_free_supported(features, patchsize, stride, pretrain_dim, target_dim, precision):
+        keep_z = True
+    q = embed_images(features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=keep_z, layernorm=layernorm)
+    groups = ops.make_groups(sizes, q.hi.device)
+    w = min_distance_weights(q, q, "unsupervised", precision, groups=groups)
+    a64, a32, X, _ = alpha_X_dist(q, w, list(taus), features, (patchsize, stride, pretrain_dim, layernorm), want_dmat=False)
     out, start = [], 0
+    Z3 = None if q.Z is None else q.Z.reshape(q.n_img, q.P, q.D)
     for n in sizes:
-        out.append(run_path([f[start:start + n] for f in features], patchsize, stride, pretrain_dim, target_dim, "unsupervised",
-                            taus, precision=precision, keep_z=keep_z))
+        sl = slice(start, start + n)
+        Dm = torch.stack([ops.pairwise_l2(X[t][sl]) for t in range(len(taus))])
+        out.append(PathResult(Z=None if Z3 is None else Z3[sl], w=w[sl], alpha64=a64[:, sl], alpha32=a32[:, sl], X=X[:, sl], Dmat=Dm,
+                              taus=list(taus), grid=q.grid))
         start += n
     return out

@@ -181,7 +181,24 @@ int ac_min_dist_sym_arg(const void* Qhi, const void* Qlo, const float* Qn2, int6
                         size_t ws_bytes, ac_stream_t stream);
 int ac_refine_min_dist(const float* Zq, const void* Qhi, const void* Qlo, int64_t Mq, const void* Bhi, const void* Blo,
                        int op_dtype, int nb_img, int P, int D, const int32_t* rowarg, const uint64_t* colkey, int sym,
-                       int q_img0, const int32_t* q_self, int Pq, float* dmin, ac_stream_t stream);
+                       int q_img0, const int32_t* q_self, int Pq, const int32_t* groups, float* dmin, ac_stream_t stream);
+
+/* ---- per-category banks in one launch sequence -------------------------------------------------------
+ * The reference runs one make_category_data per category, each with its own bank (examples/main.py:353).  The _ex
+ * forms take the images of SEVERAL categories back to back: groups[2*j], groups[2*j+1] (device int32 [nb_img, 2]) =
+ * first image and image count of the category of image j; image pairs exist only inside a category, the ownership
+ * rule of the symmetric form is applied inside it, and the reductions run over the image's own category.
+ * groups = NULL is one category (= the plain entry points).  ac_min_dist_sym_ex is the general symmetric entry point:
+ * float column minima (colmin_d2) when rowarg == colkey == NULL, else the arg-recording form (colmin_d2 unused).
+ * ac_refine_min_dist takes the same `groups` (sym = 1 only).  ac_reduce_weights_ex needs q_self when groups is given. */
+int ac_min_dist_sym_ex(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                       const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                       int bank_count, int init, float* rowmin_d2, float* colmin_d2, int32_t* rowarg, uint64_t* colkey,
+                       const int32_t* groups, void* ws, size_t ws_bytes, ac_stream_t stream);
+int ac_reduce_weights_sym_ex(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
+                             const int32_t* groups, float* w, ac_stream_t stream);
+int ac_reduce_weights_ex(const float* dmin, int64_t Mq, int nb_img, int Pq, const int32_t* q_self, const int32_t* groups,
+                         int mode, float* w, ac_stream_t stream);
 
 /* ---- stage 3 -----------------------------------------------------------------------------------
  * alpha[t, i, :] = softmax_p(w[i, :] / tau_t) in float64, max-subtracted (identical to

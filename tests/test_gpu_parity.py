@@ -488,3 +488,40 @@ def test_tau_sweep_reuses_one_distance_pass():
 
 
 # The full BASELINE sizes (configs 1, 2, 3, 5 against the oracle) live in tests/test_gpu_baseline_sizes.py.
+
+
+# ------------------------------------------------------------------------------- per-category banks in one launch
+@pytest.mark.parametrize("precision", ["f16", "f16r"])
+def test_batched_categories_equal_per_category_runs(precision):
+    """run_categories (one launch sequence, category table in the unit list -- reference semantics: one
+    make_category_data per category, main.py:353) gives exactly what separate run_path calls per category give."""
+    sizes = [5, 9, 4, 7, 2]
+    layers = [(96, 12, 12, True), (96, 12, 12, True)]
+    feats, _ = synth.planted_features(sum(sizes), layers, seed=31)
+    f = [x.cuda() for x in feats]
+    taus = [1.0, 0.25]
+    got = pipeline.run_categories(f, sizes, 3, 1, 256, 512, taus, precision=precision)
+    start = 0
+    for c, n in enumerate(sizes):
+        ref = pipeline.run_path([x[start:start + n] for x in f], 3, 1, 256, 512, "unsupervised", taus, precision=precision)
+        assert torch.equal(got[c].w, ref.w), c
+        assert torch.equal(got[c].alpha64, ref.alpha64) and torch.equal(got[c].X, ref.X) and torch.equal(got[c].Dmat, ref.Dmat)
+        assert torch.equal(got[c].Z, ref.Z)
+        start += n
+    # and against the oracle for one category
+    want = restated.full_path([x[5:14] for x in feats], 3, 1, 256, 512, 1.0, "unsupervised")
+    assert (got[1].alpha64[0].cpu() - want[2]).abs().max().item() <= 1e-3
+    assert rel_l2(got[1].X[0].cpu().numpy(), want[3]) <= 1e-3
+
+
+def test_batched_categories_config2_width_straddling_blocks():
+    """Categories whose boundaries fall inside 256-row query blocks and 32-row epilogue warps (P = 784)."""
+    sizes = [3, 4, 2]
+    layers = [(768, 28, 28, True), (768, 28, 28, True)]
+    f, _ = synth.planted_features_device(range(sum(sizes)), layers, device="cuda")
+    got = pipeline.run_categories(f, sizes, 3, 1, 2048, 4096, [1.0], precision="f16", keep_z=False)
+    start = 0
+    for c, n in enumerate(sizes):
+        ref = pipeline.run_path([x[start:start + n] for x in f], 3, 1, 2048, 4096, "unsupervised", [1.0], precision="f16", keep_z=False)
+        assert torch.equal(got[c].w, ref.w) and torch.equal(got[c].Dmat, ref.Dmat), c
+        start += n
