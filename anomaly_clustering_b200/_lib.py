@@ -84,7 +84,7 @@ SIGNATURES = {
     "ac_refine_min_dist": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
-         c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+         c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     ),
     "ac_min_dist_sym_ex": (
         c_int,

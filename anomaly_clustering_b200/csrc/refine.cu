@@ -5,11 +5,13 @@
 // its distance carries the tensor core's fp32 accumulation error over K = D products of magnitude |q||b| (systematic,
 // ~3e-3 absolute at config 2: too much for softmax(w / tau) once tau < 1).  The arg-min is far more robust than the
 // value, so that pass also records WHICH row won (ac_min_dist_arg / ac_min_dist_sym_arg) and this kernel recomputes
-//      d(r, j) = sqrt( sum_k (q_r[k] - b_(j,c)[k])^2 ),   c = arg-min row of image j for query row r,
-// in fp32 with no |x|^2+|y|^2-2xy cancellation: one gathered bank row (fp16/bf16 operand, + its lo part if present)
-// per pair against the query row held in shared memory as fp32 (from fp32 Z when the caller has it, else from the
-// operand).  What is left is the zero-mean rounding of the operands (~1e-4 per entry, averaged away by the mean over
-// bank images).  Cost: one 2*D-byte row per pair from L2 -- 64 GB at config 2 against 18 ms of GEMM.
+//      d(r, j) = || q_r - b_(j,c) ||,   c = arg-min row of image j for query row r,
+// with IEEE fp32 FMAs (round to nearest, 128 short partial sums per pair): one gathered bank row (fp16/bf16 operand, + its
+// lo part if present) per pair against the query row held in shared memory as fp32 (from fp32 Z when the caller has
+// it -- measured: the query row must NOT be the rounded operand, its rounding error is common to all bank images and
+// does not average out).  When the caller passes the bank rows' squared norms the pair costs one FFMA per element
+// (|q|^2 + |b|^2 - 2 q.b, |q|^2 summed in the kernel; the cancellation costs ~1e-6 absolute in d), else sum (q-b)^2.
+// Cost: one 2*D-byte row per pair from L2 -- 64 GB at config 2.
 //
 // Blocking: grid = (query chunks of kRQ rows, groups of Jb bank images); blocks are dispatched x-fastest, so all
 // resident blocks gather from the same Jb bank images (they stay in L2) while the query chunks stream past once per group.
@@ -19,7 +21,8 @@
 namespace ac {
 
 static constexpr int kRQ = 4;            // query rows per block (fp32 in shared memory)
-static constexpr int kRefThreads = 256;  // 8 warps: two per query row, taking alternate bank images
+static constexpr int kWPR = 4;           // warps per query row: they take every kWPR-th bank image of the group
+static constexpr int kRefThreads = kRQ * kWPR * 32;
 
 __host__ __device__ inline bool pair_owned_r(int i, int j, int N) {   // same rule as mindist_tc.cu: pair_owned
   int d = j - i;
@@ -41,6 +44,7 @@ struct RefineParams {
   int sym, q_img0;
   const int* q_self;                  // non-sym: bank index of each query image (its pair is skipped) or null
   const int* groups;                  // sym: (first image, count) of the category of every bank image, or null
+  const float* Bn2;                   // [nb_img*P] squared norms of the bank rows as gathered (hi, or hi + lo), or null
   float* dex;                         // [nb_img, Mq]
   int Jb;
 };
@@ -57,19 +61,79 @@ template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& 
   for (int i = 0; i < 4; ++i) { const float2 v = __bfloat1622float2(h[i]); f[2 * i] = v.x; f[2 * i + 1] = v.y; }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineParams p) {
+// sum_k (q[k] - b[k])^2 over one row: lane owns the 16-byte groups g = lane, lane + 32, ...  NIT > 0: trip count known
+// at compile time (D = 256 * NIT), fully unrolled -- all NIT loads of the gathered row are in flight before the first use.
+// DOT: accumulate q.b (one FFMA per element) instead of (q-b)^2.
+template <typename T, int NIT, bool LO, bool DOT>
+__device__ __forceinline__ float row_dist2(const uint4* __restrict__ bh, const uint4* __restrict__ bl, const float4* qlo4,
+                                           const float4* qhi4, int G8, int lane) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  auto body = [&](const uint4& ub, int g) {
+    float b[8];
+    unpack8<T>(ub, b);
+    if (LO) {
+      float l[8];
+      unpack8<T>(__ldg(bl + g), l);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) b[t] += l[t];
+    }
+    const float4 ql = qlo4[g], qh = qhi4[g];
+    if (DOT) {
+      a0 = fmaf(ql.x, b[0], a0); a1 = fmaf(ql.y, b[1], a1); a2 = fmaf(ql.z, b[2], a2); a3 = fmaf(ql.w, b[3], a3);
+      a0 = fmaf(qh.x, b[4], a0); a1 = fmaf(qh.y, b[5], a1); a2 = fmaf(qh.z, b[6], a2); a3 = fmaf(qh.w, b[7], a3);
+    } else {
+      float d;
+      d = ql.x - b[0]; a0 = fmaf(d, d, a0);
+      d = ql.y - b[1]; a1 = fmaf(d, d, a1);
+      d = ql.z - b[2]; a2 = fmaf(d, d, a2);
+      d = ql.w - b[3]; a3 = fmaf(d, d, a3);
+      d = qh.x - b[4]; a0 = fmaf(d, d, a0);
+      d = qh.y - b[5]; a1 = fmaf(d, d, a1);
+      d = qh.z - b[6]; a2 = fmaf(d, d, a2);
+      d = qh.w - b[7]; a3 = fmaf(d, d, a3);
+    }
+  };
+  if (NIT > 0) {
+    // batches of up to 8 independent 16-byte loads in flight per lane (the compiler barrier keeps ptxas from
+    // re-serialising them to save registers -- measured in SASS: 3 in flight without it)
+    constexpr int kBatch = NIT > 8 ? 8 : (NIT > 0 ? NIT : 1);
+#pragma unroll
+    for (int it0 = 0; it0 < NIT; it0 += kBatch) {
+      uint4 u[kBatch];
+#pragma unroll
+      for (int it = 0; it < kBatch; ++it) u[it] = __ldg(bh + lane + 32 * (it0 + it));
+      asm volatile("" ::: "memory");
+#pragma unroll
+      for (int it = 0; it < kBatch; ++it) body(u[it], lane + 32 * (it0 + it));
+    }
+  } else {
+#pragma unroll 4
+    for (int g = lane; g < G8; g += 32) body(__ldg(bh + g), g);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+template <typename T, int NIT, bool LO, bool DOT>
+__global__ void __launch_bounds__(kRefThreads, 2) refine_kernel(const RefineParams p) {
   // query rows as fp32, split so that a lane's 8 values are two conflict-free 16-byte reads:
   // element 8g+t lives in lo4[g] (t < 4) or hi4[g] (t >= 4)
   extern __shared__ __align__(16) float4 s_q[];          // [kRQ][2][D/8]
+  __shared__ float s_part[kRQ][kRefThreads / 32];
+  __shared__ float s_qn2[kRQ];
   const int G8 = p.D >> 3;
   const long long m0 = (long long)blockIdx.x * kRQ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int e = tid; e < kRQ * G8; e += kRefThreads) {
-    const int rr = e / G8, g = e - rr * G8;
+  float qacc[kRQ];                                       // DOT: this lane's share of |q|^2 per staged row
+#pragma unroll
+  for (int t = 0; t < kRQ; ++t) qacc[t] = 0.f;
+  for (int e0 = 0; e0 < kRQ * G8; e0 += kRefThreads) {
+    const int e = e0 + tid;
+    const bool on = e < kRQ * G8;
+    if (!on) break;
+    const int rr = on ? e / G8 : 0, g = e - rr * G8;
     const long long r = m0 + rr;
     float f[8];
-    if (r >= p.Mq) {
+    if (!on || r >= p.Mq) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = 0.f;
     } else if (p.Zq) {
@@ -85,12 +149,35 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineParams 
         for (int i = 0; i < 8; ++i) f[i] += l[i];
       }
     }
-    s_q[(rr * 2 + 0) * G8 + g] = make_float4(f[0], f[1], f[2], f[3]);
-    s_q[(rr * 2 + 1) * G8 + g] = make_float4(f[4], f[5], f[6], f[7]);
+    if (on) {
+      s_q[(rr * 2 + 0) * G8 + g] = make_float4(f[0], f[1], f[2], f[3]);
+      s_q[(rr * 2 + 1) * G8 + g] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    if (DOT) {
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s = fmaf(f[t], f[t], s);
+#pragma unroll
+      for (int t = 0; t < kRQ; ++t) qacc[t] += (t == rr) ? s : 0.f;
+    }
+  }
+  if (DOT) {
+    // fixed summation order (lane tree, then warps 0..15): results are bit-reproducible
+#pragma unroll
+    for (int t = 0; t < kRQ; ++t) {
+      const float v = warp_sum(qacc[t]);
+      if (lane == 0) s_part[t][warp] = v;
+    }
+    __syncthreads();
+    if (tid < kRQ) {
+      float v = 0.f;
+      for (int w = 0; w < kRefThreads / 32; ++w) v += s_part[tid][w];
+      s_qn2[tid] = v;
+    }
   }
   __syncthreads();
 
-  const int rr = warp >> 1, par = warp & 1;
+  const int rr = warp / kWPR, par = warp % kWPR;
   const long long r = m0 + rr;
   if (r >= p.Mq) return;
   const int qi = (int)(r / p.Pq);
@@ -101,7 +188,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineParams 
   // categories: only the images of the query image's own category are its bank (the rest is never read by the reduction)
   int g0 = 0, gn = p.nb_img;
   if (p.sym && p.groups) { g0 = __ldg(p.groups + 2 * i); gn = __ldg(p.groups + 2 * i + 1); }
-  for (int j = j0 + par; j < j1; j += 2) {
+  for (int j = j0 + par; j < j1; j += kWPR) {
     if (j < g0 || j >= g0 + gn) continue;
     if (j == i) {
       if (lane == 0) p.dex[(long long)j * p.Mq + r] = 0.f;     // own image: excluded by the reduction
@@ -116,32 +203,33 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineParams 
     }
     c = __shfl_sync(0xffffffffu, c, 0);
     const uint4* bh = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.Bhi) + ((long long)j * p.P + c) * p.D);
-    const uint4* bl = p.Blo ? reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.Blo) + ((long long)j * p.P + c) * p.D) : nullptr;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-    for (int g = lane; g < G8; g += 32) {
-      float b[8];
-      unpack8<T>(__ldg(bh + g), b);
-      if (bl) {
-        float l[8];
-        unpack8<T>(__ldg(bl + g), l);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) b[t] += l[t];
-      }
-      const float4 ql = qlo4[g], qh = qhi4[g];
-      float d;
-      d = ql.x - b[0]; a0 = fmaf(d, d, a0);
-      d = ql.y - b[1]; a1 = fmaf(d, d, a1);
-      d = ql.z - b[2]; a2 = fmaf(d, d, a2);
-      d = ql.w - b[3]; a3 = fmaf(d, d, a3);
-      d = qh.x - b[4]; a0 = fmaf(d, d, a0);
-      d = qh.y - b[5]; a1 = fmaf(d, d, a1);
-      d = qh.z - b[6]; a2 = fmaf(d, d, a2);
-      d = qh.w - b[7]; a3 = fmaf(d, d, a3);
-    }
-    const float s = warp_sum((a0 + a1) + (a2 + a3));
+    const uint4* bl = LO ? reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.Blo) + ((long long)j * p.P + c) * p.D) : nullptr;
+    float s = warp_sum(row_dist2<T, NIT, LO, DOT>(bh, bl, qlo4, qhi4, G8, lane));
+    if (DOT) s = fmaxf(fmaf(-2.f, s, s_qn2[rr] + __ldg(p.Bn2 + (long long)j * p.P + c)), 0.f);
     if (lane == 0) p.dex[(long long)j * p.Mq + r] = sqrtf(s);
   }
+}
+
+static int g_refine_dot = 1;   // debug knob (ac_debug_set key 6): 1 = |q|^2+|b|^2-2q.b when norms are given, 0 = always sum (q-b)^2
+
+template <typename T, int NIT, bool LO, bool DOT>
+static int launch_refine(const RefineParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  AC_CUDA(cudaFuncSetAttribute(refine_kernel<T, NIT, LO, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  refine_kernel<T, NIT, LO, DOT><<<grid, kRefThreads, smem, st>>>(p);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}
+
+template <typename T>
+static int dispatch_refine(const RefineParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  if (p.Blo) return launch_refine<T, 0, true, false>(p, grid, smem, st);      // bank given as hi + lo: generic loop
+  if (p.Bn2 && g_refine_dot) {
+    if (p.D == 4096) return launch_refine<T, 16, false, true>(p, grid, smem, st);
+    if (p.D == 1024) return launch_refine<T, 4, false, true>(p, grid, smem, st);
+    return launch_refine<T, 0, false, true>(p, grid, smem, st);
+  }
+  if (p.D == 4096) return launch_refine<T, 16, false, false>(p, grid, smem, st);
+  return launch_refine<T, 0, false, false>(p, grid, smem, st);
 }
 
 }  // namespace ac
@@ -154,10 +242,16 @@ extern "C" int ac_debug_set_refine(int mb) {
   g_refine_l2_mb = mb;
   return AC_OK;
 }
+extern "C" int ac_debug_set_refine_dot(int on) {
+  if (on != 0 && on != 1) return AC_ERR_INVALID;
+  ac::g_refine_dot = on;
+  return AC_OK;
+}
 
 extern "C" int ac_refine_min_dist(const float* Zq, const void* Qhi, const void* Qlo, int64_t Mq, const void* Bhi, const void* Blo,
                                   int op_dtype, int nb_img, int P, int D, const int32_t* rowarg, const uint64_t* colkey, int sym,
-                                  int q_img0, const int32_t* q_self, int Pq, const int32_t* groups, float* dmin, ac_stream_t stream) {
+                                  int q_img0, const int32_t* q_self, int Pq, const int32_t* groups, const float* Bn2, float* dmin,
+                                  ac_stream_t stream) {
   if ((!Zq && !Qhi) || !Bhi || !rowarg || !dmin || Mq < 0 || nb_img < 1 || P < 1 || D < 1 || Pq < 1 || q_img0 < 0) return AC_ERR_INVALID;
   if (op_dtype != AC_DT_F16 && op_dtype != AC_DT_BF16) return AC_ERR_INVALID;
   if (sym && (!colkey || Pq != P)) return AC_ERR_INVALID;
@@ -172,22 +266,15 @@ extern "C" int ac_refine_min_dist(const float* Zq, const void* Qhi, const void* 
   p.Mq = Mq; p.nb_img = nb_img; p.P = P; p.D = D; p.Pq = Pq;
   p.rowarg = rowarg; p.colkey = (const unsigned long long*)colkey; p.sym = sym; p.q_img0 = q_img0; p.q_self = q_self; p.dex = dmin;
   p.groups = sym ? groups : nullptr;
+  p.Bn2 = Bn2;
   // bank images per group: their operand rows (64 MB by default) stay L2-resident while every query chunk passes
   const double img_bytes = (double)P * D * 2.0 * (Blo ? 2 : 1);
-  p.Jb = (int)std::max(2.0, std::min(64.0, g_refine_l2_mb * 1.0e6 / img_bytes));
-  p.Jb &= ~1;                                                      // the two warps of a row take alternate images
+  p.Jb = (int)std::max((double)kWPR, std::min(64.0, g_refine_l2_mb * 1.0e6 / img_bytes));
+  p.Jb -= p.Jb % kWPR;                                             // the kWPR warps of a row take every kWPR-th image
   const long long chunks = (Mq + kRQ - 1) / kRQ;
   const int nbg = (nb_img + p.Jb - 1) / p.Jb;
   if (chunks > 0x7fffffffLL || nbg > 65535) return AC_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)chunks, (unsigned)nbg);
-  if (op_dtype == AC_DT_F16) {
-    AC_CUDA(cudaFuncSetAttribute(refine_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    refine_kernel<__half><<<grid, kRefThreads, smem, st>>>(p);
-  } else {
-    AC_CUDA(cudaFuncSetAttribute(refine_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    refine_kernel<__nv_bfloat16><<<grid, kRefThreads, smem, st>>>(p);
-  }
-  AC_LAUNCH_CHECK();
-  return AC_OK;
+  return op_dtype == AC_DT_F16 ? dispatch_refine<__half>(p, grid, smem, st) : dispatch_refine<__nv_bfloat16>(p, grid, smem, st);
 }

@@ -289,7 +289,7 @@ def run_path_sharded(
     bounds = shard_bounds(n_total, world)
     lo_i, hi_i = bounds[rank]
     z_free = (not keep_z) and hasattr(compute, "weighted_embed_from_features") and pipeline.z_free_supported(
-        local_features, patchsize, stride, pretrain_dim, target_dim, precision)
+        local_features, patchsize, stride, pretrain_dim, target_dim, precision) and precision not in pipeline.REFINED
     q = compute.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=not z_free)
     assert q.n_img == hi_i - lo_i
     P = q.P
@@ -393,7 +393,8 @@ def run_path_sharded(
         pipeline._mark("exchange_end")
         if refined:
             pipeline._mark("refine_begin")
-            dex = compute.refine_min_dist(q.Z, q.hi, q.lo, bank.hi, bank.lo, n_total, P, out[1], colkey=colfull, q_img0=lo_i)
+            dex = compute.refine_min_dist(q.Z, q.hi, q.lo, bank.hi, bank.lo, n_total, P, out[1], colkey=colfull, q_img0=lo_i,
+                                          Bn2=bank.n2)
             pipeline._mark("refine_end")
             own = torch.arange(lo_i, hi_i, dtype=torch.int32, device=dex.device)
             w = compute.reduce_weights(dex, P, own, "mean").reshape(q.n_img, P)

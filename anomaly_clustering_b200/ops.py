@@ -263,7 +263,7 @@ def min_dist_sym_arg(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: 
 
 def refine_min_dist(Zq: Optional[torch.Tensor], Qhi, Qlo, Bhi, Blo, nb_img: int, P: int, rowarg: torch.Tensor,
                     colkey: Optional[torch.Tensor] = None, q_img0: int = 0, q_self: Optional[torch.Tensor] = None,
-                    Pq: Optional[int] = None, groups: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    Pq: Optional[int] = None, groups: Optional[torch.Tensor] = None, Bn2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ac_refine_min_dist: exact fp32 distances [nb_img, Mq] of the (query row, selected bank row) pairs.
     colkey given -> symmetric form (layout [nb_img, Mq], i.e. after the column-block exchange)."""
     lib = _lib.load()
@@ -285,7 +285,7 @@ def refine_min_dist(Zq: Optional[torch.Tensor], Qhi, Qlo, Bhi, Blo, nb_img: int,
     out = torch.empty(nb_img, Mq, dtype=torch.float32, device=Bhi.device)
     rc = lib.ac_refine_min_dist(_ptr(Zq), _ptr(Qhi), _ptr(Qlo), Mq, _ptr(Bhi), _ptr(Blo), _TORCH_TO_AC[Bhi.dtype], nb_img, P, D,
                                 _ptr(rowarg), _ptr(colkey), int(sym), int(q_img0), _ptr(q_self), int(Pq or P), _ptr(groups),
-                                _ptr(out), _stream())
+                                _ptr(Bn2), _ptr(out), _stream())
     check(rc, "ac_refine_min_dist")
     return out
 

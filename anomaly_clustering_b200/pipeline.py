@@ -161,7 +161,7 @@ def min_distance_weights(
         if not refined:
             return ops.reduce_weights_sym(rowmin, colmin, q.P, 0, groups=groups).reshape(q.n_img, q.P)
         _mark("refine_begin")
-        dex = ops.refine_min_dist(q.Z, q.hi, q.lo, q.hi, q.lo, q.n_img, q.P, rowarg, colkey=colkey, q_img0=0, groups=groups)
+        dex = ops.refine_min_dist(q.Z, q.hi, q.lo, q.hi, q.lo, q.n_img, q.P, rowarg, colkey=colkey, q_img0=0, groups=groups, Bn2=q.n2)
         _mark("refine_end")
         own = torch.arange(q.n_img, dtype=torch.int32, device=dex.device)
         return ops.reduce_weights(dex, q.P, own, "mean", groups=groups).reshape(q.n_img, q.P)
@@ -180,7 +180,7 @@ def min_distance_weights(
             q_self = torch.arange(q.n_img, dtype=torch.int32, device=dmin.device)
         _mark("refine_begin")
         dmin = ops.refine_min_dist(q.Z, q.hi, q.lo, bank.hi, bank.lo, bank.n_img, bank.P, arg,
-                                   q_self=q_self if mode == "unsupervised" else None, Pq=q.P)
+                                   q_self=q_self if mode == "unsupervised" else None, Pq=q.P, Bn2=bank.n2)
         _mark("refine_end")
     if mode == "unsupervised":
         if q_self is None:
@@ -249,6 +249,8 @@ def run_path(
     precision = resolve_precision(precision, taus)
     if not keep_z and not z_free_supported(features, patchsize, stride, pretrain_dim, target_dim, precision):
         keep_z = True
+    if precision in REFINED and mode != "average":
+        keep_z = True      # the exact re-evaluation takes the QUERY rows from fp32 Z (their rounding would not average out)
     q = embed_images(features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=keep_z, layernorm=layernorm)
     w = None
     if mode == "unsupervised":
@@ -300,6 +302,8 @@ def run_categories(
             start += n
         return out
     if not keep_z and not z_free_supported(features, patchsize, stride, pretrain_dim, target_dim, precision):
+        keep_z = True
+    if precision in REFINED:
         keep_z = True
     q = embed_images(features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=keep_z, layernorm=layernorm)
     groups = ops.make_groups(sizes, q.hi.device)

@@ -466,7 +466,7 @@ def main():
         exec_flops *= 3          # three MMA passes per tile
     tflops = exec_flops / (md_ms * 1e-3) / 1e12 if md_ms > 0 else 0.0
     alg_tflops = flops / (md_ms * 1e-3) / 1e12 if md_ms > 0 else 0.0
-    z_free = (not keep_z) and feats is not None and pipeline.z_free_supported(feats, 3, 1, Dp, D, precision)
+    z_free = (not keep_z) and feats is not None and pipeline.z_free_supported(feats, 3, 1, Dp, D, precision) and precision not in pipeline.REFINED
     n_embedded = nq_local + (0 if bank is None else bank[0].shape[0])
     op_bytes = 0 if precision == "f32" else (4 if precision in ("f16x3", "bf16x3") else 2)
     embed_bytes = n_embedded * (sum(c * h * w * 4 for c, h, w, _ in layers) + P * D * op_bytes + P * 4) + (0 if z_free else nq_local * P * D * 4)

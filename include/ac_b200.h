@@ -169,7 +169,8 @@ int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_
  * operand copy Qhi (+ Qlo), the bank row from the operand copy Bhi (+ Blo).  sym = 1: query image i = q_img0 + r/P,
  * arg from rowarg where i owns the pair {i,j} else from the low half of colkey[j*Mq + r] (layout [bank image, query row],
  * i.e. after the column-block exchange); the own image gets 0.  sym = 0: arg from rowarg everywhere; q_self
- * ([ceil(Mq/Pq)] bank index of each query image, or NULL) names pairs to skip.  Feed dmin to ac_reduce_weights.
+ * ([ceil(Mq/Pq)] bank index of each query image, or NULL) names pairs to skip.  Bn2 (the bank operands' squared norms,
+ * as for ac_min_dist; may be NULL) lets a pair cost one FFMA per element.  Feed dmin to ac_reduce_weights.
  * Costs one gathered 2*D-byte row per (query row, bank image): ~1/3 of the one-pass GEMM time at config 2.
  * Needs D % 8 == 0 and D <= 12800, else AC_ERR_UNSUPPORTED (use the X3 modes). */
 int ac_min_dist_arg(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
@@ -181,7 +182,8 @@ int ac_min_dist_sym_arg(const void* Qhi, const void* Qlo, const float* Qn2, int6
                         size_t ws_bytes, ac_stream_t stream);
 int ac_refine_min_dist(const float* Zq, const void* Qhi, const void* Qlo, int64_t Mq, const void* Bhi, const void* Blo,
                        int op_dtype, int nb_img, int P, int D, const int32_t* rowarg, const uint64_t* colkey, int sym,
-                       int q_img0, const int32_t* q_self, int Pq, const int32_t* groups, float* dmin, ac_stream_t stream);
+                       int q_img0, const int32_t* q_self, int Pq, const int32_t* groups, const float* Bn2, float* dmin,
+                       ac_stream_t stream);
 
 /* ---- per-category banks in one launch sequence -------------------------------------------------------
  * The reference runs one make_category_data per category, each with its own bank (examples/main.py:353).  The _ex

@@ -296,6 +296,7 @@ def test_mindist_arg_and_refine_kernel(shape):
         # refined value from the operand rows (query side = the operand as well here): exact distance of the selected pair
     dex = ops.refine_min_dist(None, ps.hi, None, ps.hi, None, n, P, arg).double().cpu()
     dz = ops.refine_min_dist(Z.reshape(n * P, D).contiguous(), None, None, ps.hi, None, n, P, arg).double().cpu()
+    dzn = ops.refine_min_dist(Z.reshape(n * P, D).contiguous(), None, None, ps.hi, None, n, P, arg, Bn2=ps.n2).double().cpu()
     zq = Z.double().cpu().reshape(n * P, D)
     for j in range(n):
         sel = op[j][a[j]]                                              # [n*P, D] selected bank rows
@@ -303,6 +304,9 @@ def test_mindist_arg_and_refine_kernel(shape):
         assert ((dex[j] - want).abs() <= 2e-6 * want + 1e-6).all()     # fp32 sum of squares, no cancellation
         wantz = (zq - sel).norm(dim=1)
         assert ((dz[j] - wantz).abs() <= 2e-6 * wantz + 1e-6).all()    # query row taken from fp32 Z
+        off = torch.ones(n * P, dtype=torch.bool)
+        off[j * P:(j + 1) * P] = False       # |q|^2+|b|^2-2q.b form (bank norms given): cancellation only matters at d ~ 0 (own image)
+        assert ((dzn[j] - wantz).abs()[off] <= 2e-5 * wantz[off] + 1e-5).all()
 
 
 @pytest.mark.parametrize("n,P,D", [(7, 100, 256), (6, 784, 512), (5, 260, 320)])
