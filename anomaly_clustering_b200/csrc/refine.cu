@@ -236,7 +236,7 @@ static int dispatch_refine(const RefineParams& p, dim3 grid, size_t smem, cudaSt
 
 using namespace ac;
 
-static int g_refine_l2_mb = 64;   // debug knob (ac_debug_set key 5): bytes of bank operand rows one group keeps L2-resident
+static int g_refine_l2_mb = 96;   // debug knob (ac_debug_set key 5): bytes of bank operand rows one group keeps L2-resident
 extern "C" int ac_debug_set_refine(int mb) {
   if (mb < 1 || mb > 512) return AC_ERR_INVALID;
   g_refine_l2_mb = mb;
@@ -267,7 +267,7 @@ extern "C" int ac_refine_min_dist(const float* Zq, const void* Qhi, const void* 
   p.rowarg = rowarg; p.colkey = (const unsigned long long*)colkey; p.sym = sym; p.q_img0 = q_img0; p.q_self = q_self; p.dex = dmin;
   p.groups = sym ? groups : nullptr;
   p.Bn2 = Bn2;
-  // bank images per group: their operand rows (64 MB by default) stay L2-resident while every query chunk passes
+  // bank images per group: their operand rows (96 MB by default, measured best on B200) stay L2-resident while every query chunk passes
   const double img_bytes = (double)P * D * 2.0 * (Blo ? 2 : 1);
   p.Jb = (int)std::max((double)kWPR, std::min(64.0, g_refine_l2_mb * 1.0e6 / img_bytes));
   p.Jb -= p.Jb % kWPR;                                             // the kWPR warps of a row take every kWPR-th image

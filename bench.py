@@ -292,7 +292,7 @@ def run_reference_arm(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -310,7 +310,7 @@ def main():
     ap.add_argument("--z-free", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--no-symmetry", action="store_true", help="force the all-pairs distance kernel (every image pair multiplied twice)")
     ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)")
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     wl = WORKLOADS[args.workload]
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -333,7 +333,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():          # (scripts/r02_multi.py runs several workloads in one process group)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not ops.device_ok(local_rank):
@@ -602,8 +602,10 @@ def main():
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
-        os.dup2(2, 1)
-    if world > 1:
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)          # give fd 1 back (main() may be called again in this process)
+    os.close(real_stdout)
+    if world > 1 and os.environ.get("AC_BENCH_KEEP_PG", "0") != "1":
         dist.destroy_process_group()
 
 

@@ -354,7 +354,7 @@ def test_refined_sharded_slices_and_windows():
     for r, (a, b) in enumerate(bounds):
         sl = slice(a * P, b * P)
         colfull = torch.cat([parts[s][2][:, a * P:b * P] for s in range(2)], dim=0).contiguous()
-        dex = ops.refine_min_dist(ps.Z[sl], ps.hi[sl], None, ps.hi, None, n, P, parts[r][1], colkey=colfull, q_img0=a)
+        dex = ops.refine_min_dist(ps.Z[sl], ps.hi[sl], None, ps.hi, None, n, P, parts[r][1], colkey=colfull, q_img0=a, Bn2=ps.n2)
         own = torch.arange(a, b, dtype=torch.int32, device="cuda")
         w = ops.reduce_weights(dex, P, own, "mean").reshape(b - a, P)
         assert torch.equal(w, w_one[a:b])
