@@ -712,6 +712,358 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_tma_kernel(EmbedParams
 
 
 // ------------------------------------------------------------------------------------------------
+// Single-pass fused form: ONE persistent launch embeds every layer, folds the whole-map LayerNorm in without a second
+// DRAM read of the feature maps, and emits the operands' squared norms as well (default whenever all layers are
+// channel-contiguous, on one patch grid, of one width and 16-byte aligned: ViT tokens, channels_last maps).
+//
+// A work item = (image, row segment of <= kMaxSeg positions).  Items are claimed in order from a global counter; item
+// q*S + s first reduces slice s of image q (its share of sum / sum of squares for the LayerNorm statistics, patchcore.py:384)
+// and then embeds slice s of image q - LA.  An embed waits until all S slices of its image have been reduced; those
+// belong to items claimed LA*S claims earlier, which are running on resident CTAs and never wait themselves, so the
+// scheme cannot deadlock and the wait is short.  The maps of the LA + (resident items / S) images in flight (a few tens
+// of MB) stay in L2 between their statistics read (DRAM) and their 3 x 3-neighbourhood reads by the embed phase (L2).
+// Same producer-warp / mbarrier ring as embed_tma_kernel; the statistics slices travel through the same ring.
+// The LayerNorm affine is folded into the pooling: out = rstd/n * sum(raw taps) - mu*rstd with out-of-map taps set to
+// mu (the reference pads with zeros AFTER the LayerNorm), one FFMA per output instead of one per staged value.
+static constexpr int kMaxSeg = 16;
+
+struct FusedParams {
+  EmbedParams e;
+  float* n2;               // [B*P0] squared norms of the operand rows (hi [+ lo]) or null
+  double* stats;           // [B][L][S][2] partial (sum, sum of squares)
+  int* done;               // [B] slices reduced per image
+  unsigned int* counter;   // item claims
+  int S, LA, nperiods, gx, t_stride;
+  long long n_items;       // (B + LA) * S
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+
+// stores NOUT consecutive operand values (hi [+ lo]) of one patch row, returns sum (hi + lo)^2
+template <typename T, int NOUT>
+__device__ __forceinline__ float store_operand_norm(void* Zhi, void* Zlo, long long idx, bool vec, const float (&out)[NOUT]) {
+  __align__(16) T h[NOUT];
+  float nv = 0.f;
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) h[o] = to_op<T>(out[o]);
+  T* ph = reinterpret_cast<T*>(Zhi) + idx;
+  if (vec) {
+#pragma unroll
+    for (int o = 0; o + 8 <= NOUT; o += 8) *reinterpret_cast<uint4*>(ph + o) = *reinterpret_cast<const uint4*>(&h[o]);
+  } else {
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) ph[o] = h[o];
+  }
+  if (Zlo) {
+    __align__(16) T l[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+      l[o] = to_op<T>(out[o] - op_to_float(h[o]));
+      const float v = op_to_float(h[o]) + op_to_float(l[o]);
+      nv = fmaf(v, v, nv);
+    }
+    T* pl = reinterpret_cast<T*>(Zlo) + idx;
+    if (vec) {
+#pragma unroll
+      for (int o = 0; o + 8 <= NOUT; o += 8) *reinterpret_cast<uint4*>(pl + o) = *reinterpret_cast<const uint4*>(&l[o]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) pl[o] = l[o];
+    }
+  } else {
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) { const float v = op_to_float(h[o]); nv = fmaf(v, v, nv); }
+  }
+  return nv;
+}
+
+template <int A, int B, int R>
+__global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __grid_constant__ FusedParams fp) {
+  constexpr int K = 3;
+  constexpr int CPP = A / (K * K);
+  constexpr int NOUT = B / R;
+  constexpr int NCH = kThreads * CPP;
+  const EmbedParams& p = fp.e;
+  extern __shared__ __align__(128) float smem_f[];
+  float* ring = smem_f;                                    // [kRing][K][NCH]
+  float* s_nacc = smem_f + (size_t)kRing * K * NCH;        // [kMaxSeg][kThreads] per-thread share of the row norms
+  __shared__ __align__(8) uint64_t s_full[kRing], s_empty[kRing];
+  __shared__ float s_red[2][kThreads / 32];
+  __shared__ float s_mu[kMaxLayers], s_rs[kMaxLayers];
+  __shared__ long long s_item;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = (warp == kThreads / 32);
+  if (tid == 0) {
+    for (int i = 0; i < kRing; ++i) {
+      e_mbar_init(e_smem_u32(&s_full[i]), 1);
+      e_mbar_init(e_smem_u32(&s_empty[i]), kThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t jc = 0;                                         // ring column counter: identical sequence in both roles
+  const bool vec8 = (NOUT % 8 == 0) && (((p.ldz | fp.t_stride) & 7) == 0);
+  const bool vec4 = (NOUT % 4 == 0) && (((p.ldz | fp.t_stride) & 3) == 0);
+
+  for (;;) {
+    if (tid == 0) s_item = (long long)atomicAdd(fp.counter, 1u);
+    __syncthreads();
+    const long long item = s_item;
+    if (item >= fp.n_items) break;
+    const int q = (int)(item / fp.S), sg = (int)(item - (long long)q * fp.S);
+    const int y = sg / p.nxseg, xs = sg - y * p.nxseg;
+    const int xa = xs * p.xseg_len, xb = min(p.w0, xa + p.xseg_len), npos = xb - xa;
+    const int bA = (q < p.B) ? q : -1;                     // image whose statistics slice is reduced
+    const int bE = q - fp.LA;                              // image whose slice is embedded (< 0: prologue item)
+    const int nA = (npos + K - 1) / K;                     // statistics slots: K tokens each
+    const int ncols = npos + K - 1;                        // embed slots: input columns xa-1 .. xb
+
+    if (producer) {
+      // ================================================================ producer warp
+      if (lane == 0) {
+        if (bA >= 0 && p.layernorm) {
+          for (int l = 0; l < p.L; ++l) {
+            const LayerDev& ly = p.layers[l];
+            for (int cx = 0; cx < fp.gx; ++cx) {
+              const int c_start = cx * NCH;
+              const uint32_t bytes = (uint32_t)min(NCH, ly.C - c_start) * 4u;
+              const float* src = ly.ptr + (long long)(p.b0 + bA) * ly.sb + c_start + (long long)y * ly.sh + (long long)xa * ly.sw;
+              for (int t = 0; t < nA; ++t, ++jc) {
+                const uint32_t slot = jc % kRing, ph = (jc / kRing) & 1u;
+                e_mbar_wait(e_smem_u32(&s_empty[slot]), ph ^ 1u);
+                const int ntok = min(K, npos - K * t);
+                const uint32_t fb = e_smem_u32(&s_full[slot]);
+                e_mbar_expect_tx(fb, (uint32_t)ntok * bytes);
+                for (int ki = 0; ki < ntok; ++ki)
+                  e_bulk_g2s(e_smem_u32(ring + ((size_t)slot * K + ki) * NCH), src + (long long)(K * t + ki) * ly.sw, bytes, fb);
+              }
+            }
+          }
+        }
+        if (bE >= 0) {
+          for (int l = 0; l < p.L; ++l) {
+            const LayerDev& ly = p.layers[l];
+            for (int cx = 0; cx < fp.gx; ++cx) {
+              const int c_start = cx * NCH;
+              const uint32_t bytes = (uint32_t)min(NCH, ly.C - c_start) * 4u;
+              const float* src = ly.ptr + (long long)(p.b0 + bE) * ly.sb + c_start;
+              for (int j = 0; j < ncols; ++j, ++jc) {
+                const uint32_t slot = jc % kRing, ph = (jc / kRing) & 1u;
+                e_mbar_wait(e_smem_u32(&s_empty[slot]), ph ^ 1u);
+                const int ix = xa - p.pad + j;
+                const bool cin = (ix >= 0) && (ix < ly.W);
+                uint32_t nrows = 0;
+#pragma unroll
+                for (int ki = 0; ki < K; ++ki) {
+                  const int iy = y - p.pad + ki;
+                  nrows += (cin && iy >= 0 && iy < ly.H) ? 1u : 0u;
+                }
+                const uint32_t fb = e_smem_u32(&s_full[slot]);
+                if (nrows == 0) {
+                  e_mbar_arrive(fb);
+                } else {
+                  e_mbar_expect_tx(fb, nrows * bytes);
+#pragma unroll
+                  for (int ki = 0; ki < K; ++ki) {
+                    const int iy = y - p.pad + ki;
+                    if (cin && iy >= 0 && iy < ly.H)
+                      e_bulk_g2s(e_smem_u32(ring + ((size_t)slot * K + ki) * NCH), src + (long long)iy * ly.sh + (long long)ix * ly.sw, bytes, fb);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    } else {
+      // ================================================================ consumers (kThreads)
+      // ---- phase A: this item's share of the LayerNorm statistics of image bA
+      if (bA >= 0 && p.layernorm) {
+        for (int l = 0; l < p.L; ++l) {
+          float s = 0.f, qq = 0.f;
+          for (int cx = 0; cx < fp.gx; ++cx) {
+            const bool active = (cx * kThreads + tid) < fp.nperiods;
+            for (int t = 0; t < nA; ++t, ++jc) {
+              const uint32_t slot = jc % kRing, ph = (jc / kRing) & 1u;
+              e_mbar_wait(e_smem_u32(&s_full[slot]), ph);
+              const int ntok = min(K, npos - K * t);
+              if (active) {
+                const float* col = ring + (size_t)slot * K * NCH + tid * CPP;
+#pragma unroll
+                for (int ki = 0; ki < K; ++ki)
+                  if (ki < ntok) {
+#pragma unroll
+                    for (int c = 0; c < CPP; ++c) { const float v = col[ki * NCH + c]; s += v; qq = fmaf(v, v, qq); }
+                  }
+              }
+              __syncwarp();
+              if (lane == 0) e_mbar_arrive(e_smem_u32(&s_empty[slot]));
+            }
+          }
+          s = warp_sum(s);
+          qq = warp_sum(qq);
+          if (lane == 0) { s_red[0][warp] = s; s_red[1][warp] = qq; }
+          consumer_bar();
+          if (tid == 0) {
+            double a = 0, c2 = 0;
+            for (int w = 0; w < kThreads / 32; ++w) { a += (double)s_red[0][w]; c2 += (double)s_red[1][w]; }
+            double* o = fp.stats + (((long long)bA * p.L + l) * fp.S + sg) * 2;
+            o[0] = a;
+            o[1] = c2;
+          }
+          consumer_bar();
+        }
+        if (tid == 0) {
+          __threadfence();
+          atomicAdd(fp.done + bA, 1);
+        }
+      }
+      // ---- phase B: embed slice sg of image bE
+      if (bE >= 0) {
+        if (p.layernorm) {
+          if (tid == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(fp.done + bE) < fp.S) {
+              __nanosleep(100);
+              if (clock64() - t0 > 4000000000LL) __trap();     // a broken schedule must fail the launch, never hang the GPU
+            }
+          }
+          consumer_bar();
+          if (warp == 0) {
+            for (int l = 0; l < p.L; ++l) {
+              const double* st = fp.stats + (((long long)bE * p.L + l) * fp.S) * 2;
+              double a = 0, c2 = 0;
+              for (int i = lane; i < fp.S; i += 32) { a += __ldcg(st + 2 * i); c2 += __ldcg(st + 2 * i + 1); }
+              a = warp_sum(a);
+              c2 = warp_sum(c2);
+              const double n = (double)p.layers[l].C * p.layers[l].H * p.layers[l].W;
+              const double m = a / n;
+              double var = c2 / n - m * m;
+              if (var < 0) var = 0;
+              if (lane == 0) { s_mu[l] = (float)m; s_rs[l] = (float)(1.0 / sqrt(var + (double)p.eps)); }
+            }
+          }
+          consumer_bar();
+        }
+        const long long row0 = ((long long)(p.b0 + bE) * p.h0 + y) * p.w0;
+        bool first = true;
+        for (int l = 0; l < p.L; ++l) {
+          const LayerDev& ly = p.layers[l];
+          const float mu = p.layernorm ? s_mu[l] : 0.f, rs = p.layernorm ? s_rs[l] : 1.f;
+          const float nmr = -mu * rs;
+          bool rowok[K];
+#pragma unroll
+          for (int ki = 0; ki < K; ++ki) {
+            const int iy = y - p.pad + ki;
+            rowok[ki] = (iy >= 0) && (iy < ly.H);
+          }
+          for (int cx = 0; cx < fp.gx; ++cx, first = false) {
+            const int m = cx * kThreads + tid;
+            const bool active = m < fp.nperiods;
+            const int t0 = l * fp.t_stride + (active ? m : 0) * NOUT;
+            float v[CPP][K][K];   // [channel][ki][physical column slot]; out-of-map taps hold mu (= 0 after the LayerNorm)
+#pragma unroll
+            for (int c = 0; c < CPP; ++c)
+#pragma unroll
+              for (int ki = 0; ki < K; ++ki)
+#pragma unroll
+                for (int kj = 0; kj < K; ++kj) v[c][ki][kj] = mu;
+            auto step = [&](auto rot_tag, int j) {
+              constexpr int ROT = decltype(rot_tag)::value;
+              constexpr int SLOT = (ROT + K - 1) % K;
+              const uint32_t slot = jc % kRing, ph = (jc / kRing) & 1u;
+              ++jc;
+              const int ix = xa - p.pad + j;
+              const bool cin = (ix >= 0) && (ix < ly.W);
+              e_mbar_wait(e_smem_u32(&s_full[slot]), ph);
+              const float* col = ring + (size_t)slot * K * NCH + tid * CPP;
+#pragma unroll
+              for (int ki = 0; ki < K; ++ki) {
+                if (cin && rowok[ki]) {                      // warp-uniform
+#pragma unroll
+                  for (int c = 0; c < CPP; ++c) v[c][ki][SLOT] = col[ki * NCH + c];
+                } else {
+#pragma unroll
+                  for (int c = 0; c < CPP; ++c) v[c][ki][SLOT] = mu;
+                }
+              }
+              __syncwarp();
+              if (lane == 0) e_mbar_arrive(e_smem_u32(&s_empty[slot]));
+              const int x = xa + j - (K - 1);
+              if (x < xa) return;
+              float nv = 0.f;
+              if (active) {
+                float out[NOUT];
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) {
+                  float acc_o = nmr;
+#pragma unroll
+                  for (int jj = 0; jj < R; ++jj) {
+                    const int r = o * R + jj;
+                    const int f0 = (r * A) / B, f1 = ((r + 1) * A + B - 1) / B;
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int f = 0; f < A; ++f)
+                      if (f >= f0 && f < f1) sacc += v[f / (K * K)][(f % (K * K)) / K][((f % K) + ROT) % K];
+                    acc_o = fmaf(sacc, rs * (1.0f / (float)(R * (f1 - f0))), acc_o);
+                  }
+                  out[o] = acc_o;
+                }
+                const long long idx = (row0 + x) * p.ldz + t0;
+                if (p.Z) {
+                  if (vec4) {
+#pragma unroll
+                    for (int o = 0; o + 4 <= NOUT; o += 4)
+                      *reinterpret_cast<float4*>(p.Z + idx + o) = make_float4(out[o], out[o + 1], out[o + 2], out[o + 3]);
+                  } else {
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) p.Z[idx + o] = out[o];
+                  }
+                }
+                if (p.Zhi) {
+                  if (p.op_dtype == AC_DT_F16) nv = store_operand_norm<__half, NOUT>(p.Zhi, p.Zlo, idx, vec8, out);
+                  else nv = store_operand_norm<__nv_bfloat16, NOUT>(p.Zhi, p.Zlo, idx, vec8, out);
+                }
+              }
+              if (fp.n2) {
+                float* na = s_nacc + (x - xa) * kThreads + tid;
+                *na = first ? nv : (*na + nv);
+              }
+            };
+            for (int j0 = 0; j0 < ncols; j0 += 3) {
+              step(std::integral_constant<int, 1>{}, j0);
+              if (j0 + 1 < ncols) step(std::integral_constant<int, 2>{}, j0 + 1);
+              if (j0 + 2 < ncols) step(std::integral_constant<int, 0>{}, j0 + 2);
+            }
+          }
+        }
+        if (fp.n2) {
+          // squared norms of the operand rows of this segment: fixed summation order (bit-reproducible)
+          consumer_bar();
+          for (int pos = warp; pos < npos; pos += kThreads / 32) {
+            float a = 0.f;
+#pragma unroll
+            for (int k2 = 0; k2 < kThreads / 32; ++k2) a += s_nacc[pos * kThreads + lane + 32 * k2];
+            a = warp_sum(a);
+            if (lane == 0) fp.n2[row0 + xa + pos] = a;
+          }
+        }
+      }
+    }
+    __syncthreads();      // s_item / s_nacc / s_red are reused by the next item
+  }
+}
+
+__global__ void zero_words_kernel(unsigned int* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Layout / grid adapters that let every layer take the periodic fast path:
 //  * nchw_to_nhwc_kernel: CNN maps [B,C,H,W] -> channel-contiguous scratch (32x32 smem tile transpose).
 //  * upsample_store_kernel: a layer whose patch grid differs from layer 0 is pooled at ITS OWN grid into a
@@ -1138,7 +1490,7 @@ static bool periodic_instantiated(const Periodic& pr) {
   return false;
 }
 
-static int g_embed_variant = 0;   // test hook (ac_debug_set key 2): 0 = auto, 1 = force LDG periodic, 2 = force generic tap kernel
+static int g_embed_variant = 0;   // test hook (ac_debug_set key 2): 0 = auto, 1 = force LDG periodic, 2 = force generic tap kernel, 3 = per-layer TMA launches
 
 static bool tma_aligned(const EmbedParams& p, int l) {
   const LayerDev& ly = p.layers[l];
@@ -1155,7 +1507,7 @@ static int launch_periodic(EmbedParams p, const Periodic& pr, int l, int num_sms
   p.xseg_len = ceil_div(p.w0, nxseg);
   p.nxseg = ceil_div(p.w0, p.xseg_len);
   dim3 grid(gx, p.h0 * p.nxseg, p.B);
-  const bool use_tma = (g_embed_variant == 0) && tma_aligned(p, l);
+  const bool use_tma = (g_embed_variant == 0 || g_embed_variant == 3) && tma_aligned(p, l);
 #define X(a, b, r)                                                                                         \
   if (pr.A == a && pr.B == b && pr.R == r) {                                                               \
     if (use_tma) {                                                                                         \
@@ -1168,6 +1520,65 @@ static int launch_periodic(EmbedParams p, const Periodic& pr, int l, int num_sms
     }                                                                                                      \
     AC_LAUNCH_CHECK();                                                                                     \
     return AC_OK;                                                                                          \
+  }
+  AC_PERIODIC_CASES(X)
+#undef X
+  return AC_ERR_UNSUPPORTED;
+}
+
+// ---- single-pass fused form: eligibility and launch
+static int g_fused_la = 2;        // debug knob (ac_debug_set key 7): images the statistics run ahead of the embedding
+static int g_fused_cps = 3;       // debug knob (key 8): persistent CTAs per SM
+
+static bool fused_eligible(const Plan& plan, const EmbedParams& p, const Periodic* pr, int L) {
+  if (g_embed_variant != 0 || !plan.fused || p.k != 3 || p.s != 1) return false;
+  for (int l = 0; l < L; ++l) {
+    if (plan.pl[l].nchunks == 0 || !tma_aligned(p, l)) return false;
+    if (!pr[l].ok || !periodic_instantiated(pr[l]) || pr[l].transpose || pr[l].upsample) return false;
+    if (pr[l].A != pr[0].A || pr[l].B != pr[0].B || pr[l].R != pr[0].R) return false;
+    if (p.layers[l].C != p.layers[0].C || p.layers[l].H != p.layers[0].H || p.layers[l].W != p.layers[0].W) return false;
+    if (pr[l].t_base != l * pr[0].ncols) return false;
+  }
+  return true;
+}
+
+static size_t fused_ws_bytes(int L, int B, int h0, int w0) {
+  const int nxseg = ceil_div(w0, kMaxSeg);
+  const size_t S = (size_t)h0 * nxseg;
+  return (((size_t)B * L * S * 2 * sizeof(double) + 255) & ~(size_t)255) + ((((size_t)B + 64) * sizeof(int) + 255) & ~(size_t)255);
+}
+
+static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, int num_sms, cudaStream_t st) {
+  FusedParams fp;
+  memset(&fp, 0, sizeof(fp));
+  p.nxseg = ceil_div(p.w0, kMaxSeg);
+  p.xseg_len = ceil_div(p.w0, p.nxseg);
+  p.nxseg = ceil_div(p.w0, p.xseg_len);
+  p.b0 = 0;
+  fp.e = p;
+  fp.n2 = n2;
+  fp.S = p.h0 * p.nxseg;
+  fp.LA = std::max(1, std::min(g_fused_la, p.B));
+  fp.nperiods = pr.nperiods;
+  fp.gx = ceil_div(pr.nperiods, kThreads);
+  fp.t_stride = pr.ncols;
+  fp.n_items = (long long)(p.B + fp.LA) * fp.S;
+  const size_t stats_b = ((size_t)p.B * p.L * fp.S * 2 * sizeof(double) + 255) & ~(size_t)255;
+  fp.stats = (double*)ws;
+  fp.done = (int*)((char*)ws + stats_b);
+  fp.counter = (unsigned int*)(fp.done + p.B);
+  const long long words = (long long)p.B + 1;
+  zero_words_kernel<<<(unsigned)std::min<long long>((words + 255) / 256, 64), 256, 0, st>>>((unsigned int*)fp.done, words);
+  AC_LAUNCH_CHECK();
+  const int grid = (int)std::min<long long>(fp.n_items, (long long)num_sms * g_fused_cps);
+#define X(a, b, r)                                                                                                   \
+  if (pr.A == a && pr.B == b && pr.R == r) {                                                                         \
+    auto kern = embed_fused_kernel<a, b, r>;                                                                         \
+    const size_t smem = ((size_t)kRing * 3 * kThreads * (a / 9) + (size_t)kMaxSeg * kThreads) * sizeof(float);       \
+    AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+    kern<<<grid, kThreads + 32, smem, st>>>(fp);                                                                     \
+    AC_LAUNCH_CHECK();                                                                                               \
+    return AC_OK;                                                                                                    \
   }
   AC_PERIODIC_CASES(X)
 #undef X
@@ -1258,14 +1669,17 @@ extern "C" size_t ac_embed_workspace_bytes(const ac_layer_t* layers, int L, int 
     if (layers[l].sc != 1 || (long long)gh * gw != P) any_adapter = true;
   }
   size_t adapters = any_adapter ? adapter_bytes(layers, L, B, patchsize, stride, Dp, D, nullptr, nullptr) : 0;
-  return stats + chunks + concat + adapters;
+  // statistics slices + image counters of the single-pass fused form (at the end of the workspace)
+  const int gh0 = (layers[0].H + 2 * pad - (patchsize - 1) - 1) / stride + 1, gw0 = (layers[0].W + 2 * pad - (patchsize - 1) - 1) / stride + 1;
+  return stats + chunks + concat + adapters + fused_ws_bytes(L, B, gh0, gw0);
 }
 
-extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, int stride, int Dp, int D, int layernorm,
-                        float eps, float* Z, void* Zhi, void* Zlo, int op_dtype, void* ws, size_t ws_bytes,
-                        ac_stream_t stream) {
+extern "C" int ac_embed_ex(const ac_layer_t* layers, int L, int B, int patchsize, int stride, int Dp, int D, int layernorm,
+                           float eps, float* Z, void* Zhi, void* Zlo, int op_dtype, float* n2, void* ws, size_t ws_bytes,
+                           ac_stream_t stream) {
   if (!layers || !ws) return AC_ERR_INVALID;
   if (!Z && !Zhi) return AC_ERR_INVALID;
+  if (n2 && !Zhi) return AC_ERR_INVALID;
   if (Zhi && op_dtype != AC_DT_F16 && op_dtype != AC_DT_BF16) return AC_ERR_INVALID;
   if (Zlo && !Zhi) return AC_ERR_INVALID;
   if (B < 1) return AC_ERR_INVALID;
@@ -1328,6 +1742,14 @@ extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, i
   AC_CUDA(cudaGetDevice(&dev));
   AC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
 
+  // Single-pass fused form (one persistent launch: statistics, every layer, operand norms) when the shape allows it
+  if (fused_eligible(plan, p, pr, L)) {
+    const size_t fb = fused_ws_bytes(L, B, p.h0, p.w0);
+    if (fb > ws_bytes) return AC_ERR_WORKSPACE;
+    p.B = B;
+    return launch_fused(p, pr[0], n2, w8 + (ws_bytes - fb), num_sms, st);
+  }
+
   // One statistics launch and one embed launch per layer for the whole batch.  Measured on B200:
   // L2-sized sub-batches (statistics + embed sharing the maps in L2) cost more in launch tails than
   // the second HBM read of the feature maps (20 % of the traffic) saves.  grid.z is limited to 65535.
@@ -1388,13 +1810,25 @@ extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, i
       if (rc) return rc;
     }
   }
+  if (n2) return ac_row_norms(Zhi, Zlo, op_dtype, (long long)B * P0, D, n2, stream);
   return AC_OK;
 }
 
+extern "C" int ac_embed(const ac_layer_t* layers, int L, int B, int patchsize, int stride, int Dp, int D, int layernorm,
+                        float eps, float* Z, void* Zhi, void* Zlo, int op_dtype, void* ws, size_t ws_bytes,
+                        ac_stream_t stream) {
+  return ac_embed_ex(layers, L, B, patchsize, stride, Dp, D, layernorm, eps, Z, Zhi, Zlo, op_dtype, nullptr, ws, ws_bytes, stream);
+}
+
 extern "C" int ac_debug_set_embed(int value) {
-  if (value < 0 || value > 2) return AC_ERR_INVALID;
+  if (value < 0 || value > 3) return AC_ERR_INVALID;   // 3 = per-layer launches (TMA kernel where it applies), never the fused form
   g_embed_variant = value;
   return AC_OK;
+}
+extern "C" int ac_debug_set_fused(int key, int value) {
+  if (key == 7 && value >= 1 && value <= 64) { g_fused_la = value; return AC_OK; }
+  if (key == 8 && value >= 1 && value <= 3) { g_fused_cps = value; return AC_OK; }
+  return AC_ERR_INVALID;
 }
 
 extern "C" size_t ac_weighted_embed_from_features_workspace_bytes(const ac_layer_t* layers, int L, int B, int patchsize) {

@@ -99,8 +99,10 @@ def embed(
     out_z: Optional[torch.Tensor] = None,
     out_hi: Optional[torch.Tensor] = None,
     out_lo: Optional[torch.Tensor] = None,
+    out_n2: Optional[torch.Tensor] = None,
 ):
-    """Fused stage 1.  Returns (Z [B*P, D] fp32 | None, Zhi | None, Zlo | None, (h, w))."""
+    """Fused stage 1.  Returns (Z [B*P, D] fp32 | None, Zhi | None, Zlo | None, (h, w)).  out_n2 [B*P] fp32 (needs an
+    operand) receives the squared norms of the operand rows (ac_embed_ex)."""
     lib = _lib.load()
     views = [feature_view(f) for f in features]
     _need_cuda(*views)
@@ -128,8 +130,10 @@ def embed(
             lo = out_lo if out_lo is not None else torch.empty(rows, target_dim, dtype=tdt, device=dev)
     ws_bytes = lib.ac_embed_workspace_bytes(arr, L, B, patchsize, stride, pretrain_dim, target_dim)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    rc = lib.ac_embed(arr, L, B, patchsize, stride, pretrain_dim, target_dim, int(layernorm), float(eps), _ptr(Z), _ptr(hi),
-                      _ptr(lo), op_code, _ptr(ws), ws_bytes, _stream())
+    if out_n2 is not None:
+        assert hi is not None and out_n2.dtype == torch.float32 and out_n2.numel() == rows and out_n2.is_contiguous()
+    rc = lib.ac_embed_ex(arr, L, B, patchsize, stride, pretrain_dim, target_dim, int(layernorm), float(eps), _ptr(Z), _ptr(hi),
+                         _ptr(lo), op_code, _ptr(out_n2), _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_embed")
     return Z, hi, lo, (h, w)
 

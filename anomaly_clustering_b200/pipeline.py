@@ -92,9 +92,8 @@ def embed_images(
     layernorm: bool = True,
     batch: Optional[int] = None,
 ) -> PatchSet:
-    """Stage 1 for a set of images in one C-ABI call (the library itself walks the images in
-    L2-sized sub-batches so the LayerNorm statistics pass and the fused embed kernel share the
-    feature maps in L2); `batch` only caps the images per call."""
+    """Stage 1 for a set of images in one C-ABI call (ac_embed_ex: Z and / or the tensor-core operands, and the operands'
+    squared norms); `batch` only caps the images per call."""
     operand, want_lo = _OPERAND_OF[precision]
     views = [ops.feature_view(f) for f in features]
     N = views[0].shape[0]
@@ -109,6 +108,7 @@ def embed_images(
         tdt = torch.float16 if operand == "f16" else torch.bfloat16
         hi = torch.empty(N * P, target_dim, dtype=tdt, device=dev)
         lo = torch.empty(N * P, target_dim, dtype=tdt, device=dev) if want_lo else None
+    n2 = torch.empty(N * P, dtype=torch.float32, device=dev) if operand is not None else None
     step = N if not batch else batch
     for b0 in range(0, N, step):
         b1 = min(N, b0 + step)
@@ -117,12 +117,10 @@ def embed_images(
             [v[b0:b1] for v in views], patchsize, stride, pretrain_dim, target_dim, layernorm=layernorm,
             want_z=need_z, operand=operand, want_lo=want_lo,
             out_z=None if Z is None else Z[sl], out_hi=None if hi is None else hi[sl], out_lo=None if lo is None else lo[sl],
+            out_n2=None if n2 is None else n2[sl],
         )
     _mark("embed_end")
-    ps = PatchSet(n_img=N, P=P, D=target_dim, grid=(h, w), Z=Z, hi=hi, lo=lo)
-    if operand is not None:
-        ps.n2 = ops.row_norms(hi, lo)
-    return ps
+    return PatchSet(n_img=N, P=P, D=target_dim, grid=(h, w), Z=Z, hi=hi, lo=lo, n2=n2)
 
 
 def patchset_from_Z(Z: torch.Tensor, precision: str = "f16") -> PatchSet:

@@ -87,6 +87,12 @@ size_t ac_embed_workspace_bytes(const ac_layer_t* layers_host, int L, int B, int
 int ac_embed(const ac_layer_t* layers_host, int L, int B, int patchsize, int stride, int Dp, int D,
              int layernorm, float eps, float* Z, void* Zhi, void* Zlo, int op_dtype, void* ws,
              size_t ws_bytes, ac_stream_t stream);
+/* Same, and n2 [B*P] (may be NULL) receives the squared norms of the operand rows (hi, or hi + lo) that
+ * ac_min_dist needs -- emitted by the embed kernel itself when the single-pass fused form applies (all layers
+ * channel-contiguous, of one shape, 16-byte aligned: ViT tokens), by ac_row_norms otherwise.  Needs Zhi. */
+int ac_embed_ex(const ac_layer_t* layers_host, int L, int B, int patchsize, int stride, int Dp, int D,
+                int layernorm, float eps, float* Z, void* Zhi, void* Zlo, int op_dtype, float* n2, void* ws,
+                size_t ws_bytes, ac_stream_t stream);
 
 /* PatchMaker.patchify standalone (models/patchcore/patchcore.py:439-465):
  * x [B,C,H,W] contiguous -> out [B, h*w, C, k, k]; grid_host[2] receives (h, w). */
