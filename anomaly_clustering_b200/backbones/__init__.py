@@ -12,8 +12,24 @@ import torch
 from .vit import VisionTransformer, vit_base, vit_small  # noqa: F401
 
 
-def load(name: str, seed: int = 2023) -> torch.nn.Module:
-    """name: 'wideresnet50' | 'dino_vitbase8' | 'dino_vitsmall8' | 'dino_vitbase16' (random init)."""
+class RandomInitBackboneWarning(UserWarning):
+    pass
+
+
+def load(name: str, seed: int = 2023, allow_random_init: bool = False) -> torch.nn.Module:
+    """name: 'wideresnet50' | 'dino_vitbase8' | 'dino_vitsmall8' | 'dino_vitbase16'.
+
+    The networks are RANDOM-INIT (the reference's `patchcore.backbones.load` downloads pretrained DINO / ImageNet
+    weights, backbones.py:56-79, which is impossible offline): alpha / X / NMI computed from them are meaningless for
+    real data.  The caller must say so explicitly (`allow_random_init=True`); a warning is emitted either way and the
+    returned module carries `random_init = True` so that drivers can tag their output."""
+    import warnings
+
+    if not allow_random_init:
+        raise ValueError("backbones.load(%r) builds a RANDOM-INIT network (no pretrained weights offline). Pass a pretrained "
+                         "torch module as `backbone=` instead, or allow_random_init=True for shape / smoke runs." % name)
+    warnings.warn("backbone %r is RANDOM-INIT: results are for shape / performance checks only, not for real data" % name,
+                  RandomInitBackboneWarning, stacklevel=2)
     gen_state = torch.random.get_rng_state()
     torch.manual_seed(seed)
     try:
@@ -32,4 +48,5 @@ def load(name: str, seed: int = 2023) -> torch.nn.Module:
     finally:
         torch.random.set_rng_state(gen_state)
     net.name = name
+    net.random_init = True
     return net.eval()

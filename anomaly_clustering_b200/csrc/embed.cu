@@ -1671,7 +1671,7 @@ extern "C" size_t ac_embed_workspace_bytes(const ac_layer_t* layers, int L, int 
   size_t adapters = any_adapter ? adapter_bytes(layers, L, B, patchsize, stride, Dp, D, nullptr, nullptr) : 0;
   // statistics slices + image counters of the single-pass fused form (at the end of the workspace)
   const int gh0 = (layers[0].H + 2 * pad - (patchsize - 1) - 1) / stride + 1, gw0 = (layers[0].W + 2 * pad - (patchsize - 1) - 1) / stride + 1;
-  return stats + chunks + concat + adapters + fused_ws_bytes(L, B, gh0, gw0);
+  return stats + chunks + concat + adapters + fused_ws_bytes(L, B, gh0, gw0) + 256;
 }
 
 extern "C" int ac_embed_ex(const ac_layer_t* layers, int L, int B, int patchsize, int stride, int Dp, int D, int layernorm,
@@ -1744,10 +1744,10 @@ extern "C" int ac_embed_ex(const ac_layer_t* layers, int L, int B, int patchsize
 
   // Single-pass fused form (one persistent launch: statistics, every layer, operand norms) when the shape allows it
   if (fused_eligible(plan, p, pr, L)) {
-    const size_t fb = fused_ws_bytes(L, B, p.h0, p.w0);
-    if (fb > ws_bytes) return AC_ERR_WORKSPACE;
+    const size_t fb = fused_ws_bytes(L, B, p.h0, p.w0) + 256;
+    if (fb > ws_bytes || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return AC_ERR_WORKSPACE;
     p.B = B;
-    return launch_fused(p, pr[0], n2, w8 + (ws_bytes - fb), num_sms, st);
+    return launch_fused(p, pr[0], n2, w8 + ((ws_bytes - fb) & ~(size_t)255), num_sms, st);
   }
 
   // One statistics launch and one embed launch per layer for the whole batch.  Measured on B200:

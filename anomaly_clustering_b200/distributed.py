@@ -177,6 +177,36 @@ def shard_pipeline_plan(need: Sequence[Sequence[int]], rank: int, world: int) ->
     return plan
 
 
+@functools.lru_cache(maxsize=256)
+def plan_pull_windows(bounds: Tuple[Tuple[int, int], ...], n_total: int, rank: int, order: Tuple[int, ...], P: int, D: int,
+                      row_bytes: int, pull_gbps: float = 600.0, gemm_tflops: float = 1300.0) -> Tuple[Tuple[int, ...], ...]:
+    """Groups the shards that arrive in ring order `order` into GEMM launches: a launch takes every shard expected to have
+    landed when the previous launch ends (at least one), so that the kernel never waits for data it could have been
+    given later and no launch is smaller than it has to be.  Estimates: copy-engine pulls at `pull_gbps`, the symmetric
+    kernel at `gemm_tflops` on the pairs this rank owns.  Pure host logic (cached); returns tuples of source ranks."""
+    a, b = bounds[rank]
+
+    def pairs(src):
+        sa, sb = bounds[src]
+        return sum(pair_owned(i, j, n_total) for i in range(a, b) for j in range(sa, sb))
+
+    t = pairs(rank) * 2.0 * P * P * D / (gemm_tflops * 1e12)            # the local window runs first
+    landed, acc = [], 0.0
+    for src in order:
+        acc += (bounds[src][1] - bounds[src][0]) * P * row_bytes / (pull_gbps * 1e9)
+        landed.append(acc)
+    groups, k = [], 0
+    while k < len(order):
+        take = [order[k]]
+        k += 1
+        while k < len(order) and landed[k] <= t:
+            take.append(order[k])
+            k += 1
+        t = max(t, landed[k - 1]) + sum(pairs(s_) for s_ in take) * 2.0 * P * P * D / (gemm_tflops * 1e12)
+        groups.append(tuple(take))
+    return tuple(groups)
+
+
 def start_all_gather_rows(local: torch.Tensor, counts: Sequence[int], group=None):
     """Asynchronous all-gather of row blocks into one buffer whose local slice is already valid, so work on
     the local shard can overlap the collective.  Returns (buffer, [work])."""
@@ -274,6 +304,7 @@ def run_path_sharded(
             pairwise_l2 = staticmethod(ops.pairwise_l2)
             min_dist_sym = staticmethod(ops.min_dist_sym)
             supports_bank_window = True
+            is_cuda_backend = True
             weighted_embed_from_features = staticmethod(ops.weighted_embed_from_features)
             reduce_weights_sym = staticmethod(ops.reduce_weights_sym)
             min_dist_sym_arg = staticmethod(ops.min_dist_sym_arg)
@@ -288,17 +319,46 @@ def run_path_sharded(
         raise ValueError("run_path_sharded: %d images over %d ranks leaves empty shards; use a smaller group" % (n_total, world))
     bounds = shard_bounds(n_total, world)
     lo_i, hi_i = bounds[rank]
+    compute_is_cuda = getattr(compute, "is_cuda_backend", False)
     z_free = (not keep_z) and hasattr(compute, "weighted_embed_from_features") and pipeline.z_free_supported(
         local_features, patchsize, stride, pretrain_dim, target_dim, precision) and precision not in pipeline.REFINED
-    q = compute.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=not z_free)
+    refined = precision in pipeline.REFINED
+    # transport of the operand shards: copy-engine pulls from symmetric memory (symm_transport.py) on NCCL / CUDA groups
+    # with the CUDA back-end; NCCL collectives otherwise (AC_SHARD_TRANSPORT=nccl forces them)
+    views0 = local_features[0]
+    P_guess = None
+    symm_bank = None
+    want_symm = (symmetric and compute_is_cuda and world > 1 and dist.get_backend(group) == "nccl" and precision != "f32"
+                 and os.environ.get("AC_SHARD_TRANSPORT", "symm") == "symm")
+    if want_symm:
+        from . import ops as _ops
+        from .symm_transport import SymmetricBank
+
+        v0 = _ops.feature_view(views0)
+        gh, gw = _ops.patch_grid(v0.shape[2], v0.shape[3], patchsize, stride)
+        P_guess = gh * gw
+        if P_guess >= 32 and SymmetricBank.disabled_reason is None:
+            operand, want_lo = pipeline._OPERAND_OF[precision]
+            try:
+                symm_bank = SymmetricBank.get(n_total * P_guess, target_dim, torch.float16 if operand == "f16" else torch.bfloat16,
+                                              want_lo, v0.device, group)
+            except Exception as e:  # noqa: BLE001 -- symmetric memory unavailable on this system: say so once, use NCCL
+                SymmetricBank.disabled_reason = repr(e)
+                import warnings
+
+                warnings.warn("symmetric-memory transport unavailable (%r): the sharded path uses NCCL collectives" % (e,))
+    if symm_bank is not None:
+        outs = symm_bank.local_slices(lo_i * P_guess, hi_i * P_guess)
+        q = compute.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=not z_free, out=outs)
+    else:
+        q = compute.embed_images(local_features, patchsize, stride, pretrain_dim, target_dim, precision, want_z=not z_free)
     assert q.n_img == hi_i - lo_i
     P = q.P
     row_counts = [(b - a) * P for a, b in bounds]
     use_sym = symmetric and precision != "f32" and P >= 32 and hasattr(compute, "min_dist_sym")
     # refined modes ('f16r'): the tensor-core pass records arg-mins, ac_refine_min_dist re-evaluates the selected pairs
-    # exactly.  Every rank refines ALL (own row, other image) entries, so it needs the whole bank (full gather) and the
+    # exactly.  Every rank refines ALL (own row, other image) entries, so it needs the whole bank (every shard) and the
     # (distance, row) keys of the column minima travel instead of the float minima.
-    refined = precision in pipeline.REFINED
     if refined and not (use_sym and hasattr(compute, "min_dist_sym_arg")):
         raise ValueError("precision %r needs the symmetric sharded path" % precision)
     sym_launch = compute.min_dist_sym_arg if refined else compute.min_dist_sym
@@ -306,17 +366,16 @@ def run_path_sharded(
     pending = []
     pipeline_steps = None
     # opt-in (AC_SHARD_PIPELINE=1): shard-granular pipeline -- multiply against shard k while shards k+1.. travel
-    shard_pipeline = (use_sym and world > 2 and os.environ.get("AC_SHARD_PIPELINE", "0") == "1" and not refined
-                      and getattr(compute, "supports_bank_window", False))
+    shard_pipeline = use_sym and getattr(compute, "supports_bank_window", False) and (
+        symm_bank is not None or (world > 2 and os.environ.get("AC_SHARD_PIPELINE", "0") == "1" and not refined))
+    if symm_bank is not None and not shard_pipeline:
+        raise RuntimeError("symmetric transport chosen for a shape the windowed kernel does not take")
     if shard_pipeline:
         need_all = needed_shards(bounds, n_total)
-        if os.environ.get("AC_SHARD_TRANSPORT", "nccl") == "symm" and dist.get_backend(group) == "nccl":
-            # copy-engine pulls from symmetric memory instead of NCCL send/recv kernels (symm_transport.py; not yet
-            # run on hardware -- opt-in only)
-            from .symm_transport import SymmetricBank
-
-            sb_ = SymmetricBank.get(n_total * P, q.D, q.hi.dtype, q.lo is not None, q.hi.device, group)
-            (hi_buf, lo_buf, n2_buf), pipeline_steps = sb_.start(q.hi, q.lo, q.n2, bounds, P, need_all[rank], rank, world)
+        if symm_bank is not None:
+            # every shard for the refined modes (each rank re-evaluates all of its rows against the whole bank)
+            need_rank = [r for r in range(world) if r != rank] if refined else need_all[rank]
+            (hi_buf, lo_buf, n2_buf), pipeline_steps = symm_bank.publish_and_pull(bounds, P, need_rank, rank, world)
         else:
             (hi_buf, lo_buf, n2_buf), pipeline_steps = start_shard_pipeline([q.hi, q.lo, q.n2], bounds, P, need_all, group)
         bank = pipeline.PatchSet(n_total, P, q.D, q.grid, hi=hi_buf, lo=lo_buf, n2=n2_buf)
@@ -357,8 +416,18 @@ def run_path_sharded(
         two_phase = bool(pending) and q.n_img > 1 and world >= min_world and getattr(compute, "supports_bank_window", False)
         if shard_pipeline:
             windows = [((lo_i, q.n_img), [])] if q.n_img > 1 else []          # the local shard needs no transfer
-            for src, reqs in pipeline_steps:
-                windows.append((None if src is None else (bounds[src][0], bounds[src][1] - bounds[src][0]), reqs))
+            if symm_bank is not None and pipeline_steps and os.environ.get("AC_SHARD_MERGE", "1") == "1":
+                # copy-engine pulls land faster than the GEMM consumes them: merge the shards that will have landed
+                # anyway into one launch (consecutive ring shards form one circular window of bank images)
+                by_src = dict(pipeline_steps)
+                order = tuple(src for src, _ in pipeline_steps)
+                row_bytes = q.D * q.hi.element_size() * (2 if q.lo is not None else 1)
+                for grp in plan_pull_windows(tuple(tuple(b_) for b_ in bounds), n_total, rank, order, P, q.D, row_bytes):
+                    count = sum(bounds[s_][1] - bounds[s_][0] for s_ in grp)
+                    windows.append(((bounds[grp[0]][0], count), by_src[grp[-1]]))  # the last shard's event covers the group
+            else:
+                for src, reqs in pipeline_steps:
+                    windows.append((None if src is None else (bounds[src][0], bounds[src][1] - bounds[src][0]), reqs))
             out, first = None, True
             for window, reqs in windows:
                 for r in reqs:
@@ -366,8 +435,8 @@ def run_path_sharded(
                 if window is None:
                     continue
                 pipeline._mark("mindist_begin")
-                out = compute.min_dist_sym(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,
-                                           bank_window=window, init=first, out=out)
+                out = sym_launch(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision,
+                                 bank_window=window, init=first, out=out)
                 pipeline._mark("mindist_end")
                 first = False
         elif two_phase:

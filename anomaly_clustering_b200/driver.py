@@ -52,19 +52,29 @@ def make_category_data(
     input_shape=(3, 224, 224),
     info_root: Optional[str] = None,
     keep_weights: bool = False,
+    allow_random_init: bool = False,
 ):
     """Returns (matrix_alpha [N,1,P] f32 device tensor, X [N,D] f32 ndarray) for a scalar tau, a list of
     such tuples for a list of taus, and writes the reference's pickle(s) when `save_path` is given.
     `info_root` (the reference's `outputs` directory) also writes <info_root>/<dataset>/info/info_<category>.pickle
     from the loader's non-image fields (main.py:253-262, the file test.py:156 reads); `keep_weights` stores the
-    tau-independent weights next to the pickles so a later tau sweep can skip the distance pass."""
+    tau-independent weights next to the pickles so a later tau sweep can skip the distance pass.
+    `backbone` (a torch module with the reference's pretrained weights loaded) is REQUIRED: the offline stand-ins of
+    `backbones.load` are random-init and would silently write meaningless results under the reference's file names.
+    `allow_random_init=True` permits them for shape / smoke runs (the CLI then tags the backbone directory `-randinit`)."""
     if test_dataloader is None:
         raise ValueError("inject test_dataloader: the MVTec walker (datasets/mvtec.py) is out of scope and `path` is not read")
     device = device or torch.device("cuda", torch.cuda.current_device())
     if backbone is None:
+        if not allow_random_init:
+            raise ValueError("make_category_data needs `backbone=` (a pretrained torch module; the reference downloads DINO / ImageNet "
+                             "weights, backbones.py:56-79).  For a shape / smoke run with a RANDOM-INIT network pass allow_random_init=True.")
         from . import backbones
 
-        backbone = backbones.load(backbone_names[0])
+        backbone = backbones.load(backbone_names[0], allow_random_init=True)
+    elif getattr(backbone, "random_init", False) and not allow_random_init:
+        raise ValueError("the injected backbone is a RANDOM-INIT stand-in (backbones.load); pass allow_random_init=True for a shape / "
+                         "smoke run, or a module with the pretrained weights loaded")
     core = AnomalyClusteringCore(device).load(
         backbone=backbone, layers_to_extract_from=layers_to_extract_from, device=device, input_shape=input_shape,
         pretrain_embed_dimension=pretrain_embed_dimension, target_embed_dimension=target_embed_dimension, patchsize=patchsize,

@@ -22,7 +22,9 @@ def save_matrix_alpha_X(save_path, layers, pretrain_dim, target_dim, tau, train_
     a = torch.as_tensor(matrix_alpha).detach()
     if a.dim() == 2:
         a = a.unsqueeze(1)
-    a = a.float()
+    # own, compact CPU storage: torch.save serialises the WHOLE underlying storage of a view (a slice of the [T,N,P]
+    # alpha tensor would drag every other tau's alpha into each file), and the reference's pickles load without CUDA
+    a = a.float().cpu().contiguous().clone()
     Xn = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X)
     path = os.path.join(d, "matrix_alpha_X_" + category + "_" + supervised + ".pickle")
     torch.save((a, Xn.astype(np.float32)), path)

@@ -80,8 +80,10 @@ def main(argv=None):
         raise SystemExit("only --dataset synthetic is available offline; for real data call "
                          "anomaly_clustering_b200.driver.make_category_data(..., test_dataloader=..., backbone=...)")
     device = _device()
-    net = backbones.load(args.backbone_names[0])
-    save_path = os.path.join(args.output_dir, args.dataset, args.backbone_names[0], args.supervised)
+    # --dataset synthetic is a shape / smoke run by construction: random-init network, said loudly, tagged output directory
+    net = backbones.load(args.backbone_names[0], allow_random_init=True)
+    backbone_dir = args.backbone_names[0] + ("-randinit" if getattr(net, "random_init", True) else "")   # never the reference's own name
+    save_path = os.path.join(args.output_dir, args.dataset, backbone_dir, args.supervised)
     os.makedirs(save_path, exist_ok=True)
     rows = []
     for ci, category in enumerate(args.categories):
@@ -94,7 +96,7 @@ def main(argv=None):
                                         train_ratio=args.train_ratio, tau=list(args.tau), supervised=args.supervised,
                                         dataset=args.dataset, test_dataloader=loader, train_dataloader=train, backbone=net,
                                         device=device, precision=args.precision,
-                                        info_root=args.output_dir)
+                                        info_root=args.output_dir, allow_random_init=True)
         from . import ops
 
         for (alpha, X), tau in zip(res, args.tau):

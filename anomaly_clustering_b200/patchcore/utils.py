@@ -13,9 +13,15 @@ import torch
 
 from .. import ops, pipeline
 
-PRECISION = "auto"  # auto | f16 | bf16 | f16x3 | bf16x3 | f32; auto = f16, or f16x3 for 0 < tau < 0.5
+PRECISION = "auto"  # auto | f16 | f16r | bf16 | f16x3 | bf16x3 | f32; auto = f16 for tau >= 1, else f16r
 
 _cache: Dict[str, tuple] = {}
+
+
+def clear_cache() -> None:
+    """Drops the cached tensor-core operands of the last Z (they hold a view of the caller's Z plus an fp16 copy: about
+    2 GB at config 2).  The cache only exists because the reference API is invoked once per image."""
+    _cache.clear()
 
 
 def _patchset(Z: torch.Tensor, precision: str) -> pipeline.PatchSet:

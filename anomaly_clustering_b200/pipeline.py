@@ -91,9 +91,11 @@ def embed_images(
     want_z: bool = True,
     layernorm: bool = True,
     batch: Optional[int] = None,
+    out=None,
 ) -> PatchSet:
     """Stage 1 for a set of images in one C-ABI call (ac_embed_ex: Z and / or the tensor-core operands, and the operands'
-    squared norms); `batch` only caps the images per call."""
+    squared norms); `batch` only caps the images per call.  `out` = (hi, lo | None, n2) preallocated operand buffers (the
+    sharded path hands in its slice of the symmetric bank so that no staging copy is needed)."""
     operand, want_lo = _OPERAND_OF[precision]
     views = [ops.feature_view(f) for f in features]
     N = views[0].shape[0]
@@ -103,12 +105,17 @@ def embed_images(
     dev = views[0].device
     need_z = want_z or operand is None
     Z = torch.empty(N * P, target_dim, dtype=torch.float32, device=dev) if need_z else None
-    hi = lo = None
+    hi = lo = n2 = None
     if operand is not None:
         tdt = torch.float16 if operand == "f16" else torch.bfloat16
-        hi = torch.empty(N * P, target_dim, dtype=tdt, device=dev)
-        lo = torch.empty(N * P, target_dim, dtype=tdt, device=dev) if want_lo else None
-    n2 = torch.empty(N * P, dtype=torch.float32, device=dev) if operand is not None else None
+        if out is not None:
+            hi, lo, n2 = out
+            assert hi.shape == (N * P, target_dim) and hi.dtype == tdt and hi.is_contiguous() and n2.shape == (N * P,)
+            assert (lo is not None) == want_lo
+        else:
+            hi = torch.empty(N * P, target_dim, dtype=tdt, device=dev)
+            lo = torch.empty(N * P, target_dim, dtype=tdt, device=dev) if want_lo else None
+            n2 = torch.empty(N * P, dtype=torch.float32, device=dev)
     step = N if not batch else batch
     for b0 in range(0, N, step):
         b1 = min(N, b0 + step)

@@ -1,22 +1,20 @@
-"""Copy-engine transport of the tensor-core operands for the sharded path (opt-in: AC_SHARD_PIPELINE=1 and
-AC_SHARD_TRANSPORT=symm).
+"""Copy-engine transport of the tensor-core operands for the sharded path (default on NCCL / CUDA groups;
+AC_SHARD_TRANSPORT=nccl switches back to NCCL collectives).
 
-STATUS: written at the end of round 1 after the GPU budget was spent -- NOT yet run on a B200.  It is never
-selected by default; DESIGN.md section 8 item 2 is the plan it implements.
+Why (measured at 8 B200, config 2, profiles/r02_timeline_*): NCCL moves a rank's 80 MB operand shard at 120-140 GB/s
+through its send/recv kernels and the uneven all-gather (grouped broadcasts, LL protocol) needs 1.2 ms for 562 MB -- both
+slower than the 0.6 ms GEMM that consumes a shard, so the min-distance kernel waited for data.  With the bank buffers
+allocated as torch symmetric memory (CUDA VMM allocations mapped into every rank of the node over NVLink / NVSwitch)
 
-Why: NCCL's send/recv kernels occupy SMs while the persistent min-distance GEMM is running.  With the bank
-buffers allocated as torch symmetric memory (CUDA VMM allocations mapped into every rank of the node over
-NVLink / NVSwitch), a rank PULLS the shards it needs with plain device-to-device copies from the peer mapping:
-those run on the copy engines, cost no SM, and each shard gets its own event, so the GEMM launch for shard k
-starts as soon as shard k has landed while shards k+1.. are still in flight.
+  * the embed kernel writes its operands and norms STRAIGHT into this rank's slice of the symmetric bank (no staging copy),
+  * one device-side barrier publishes the slices,
+  * every rank PULLS the shards it needs from the peer mappings with plain device-to-device copies on a side stream:
+    they run on the copy engines at NVLink speed, cost no SM while the persistent GEMM is running, and each shard has
+    its own event, so the GEMM window of shard k starts as soon as shard k has landed (ring order rank+1, rank+2, ...).
 
-Ordering (all stream-ordered, no host synchronisation):
-  barrier A   peers have finished pulling my slice of the PREVIOUS step (their main stream waited for their pull
-              events before it reached this barrier)          -> I may overwrite my slice
-  local copy  my operands -> my slice of the symmetric buffers
-  barrier B   every rank's slice is written                   -> pulls may start
-  pulls       side stream, ring order (rank+1, rank+2, ...), one event per source shard
-"""
+Two buffer sets alternate between steps, so ONE barrier per step is enough: a rank reaches the barrier of step t+1 only
+after its stream has consumed every shard it pulled in step t, hence after that barrier the set of step t may be
+overwritten (that happens in step t+2)."""
 from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
@@ -35,9 +33,10 @@ class _EventRequest:
 
 
 class SymmetricBank:
-    """Persistent symmetric buffers for (hi, lo, n2) of the WHOLE bank, one set per (rows, D, dtype, lo?, group)."""
+    """Persistent symmetric buffers for (hi, lo, n2) of the WHOLE bank, two sets per (rows, D, dtype, lo?, group)."""
 
     _cache = {}
+    disabled_reason: Optional[str] = None          # set when the symmetric-memory set-up failed once (NCCL transport is used)
 
     @classmethod
     def get(cls, total_rows: int, D: int, dtype: torch.dtype, want_lo: bool, device, group) -> "SymmetricBank":
@@ -46,6 +45,8 @@ class SymmetricBank:
         g = group if group is not None else dist.group.WORLD
         key = (total_rows, D, dtype, want_lo, str(device), g.group_name)
         if key not in cls._cache:
+            if len(cls._cache) >= 4:               # shapes change rarely; do not hoard VMM mappings
+                cls._cache.clear()
             cls._cache[key] = cls(total_rows, D, dtype, want_lo, device, g)
         return cls._cache[key]
 
@@ -53,23 +54,35 @@ class SymmetricBank:
         import torch.distributed._symmetric_memory as symm
 
         self.group = group
-        self.hi = symm.empty((total_rows, D), dtype=dtype, device=device)
-        self.lo = symm.empty((total_rows, D), dtype=dtype, device=device) if want_lo else None
-        self.n2 = symm.empty((total_rows,), dtype=torch.float32, device=device)
-        self.handles = [None if t is None else symm.rendezvous(t, group) for t in (self.hi, self.lo, self.n2)]   # collective
+        self.sets = []
+        for _ in range(2):
+            hi = symm.empty((total_rows, D), dtype=dtype, device=device)
+            lo = symm.empty((total_rows, D), dtype=dtype, device=device) if want_lo else None
+            n2 = symm.empty((total_rows,), dtype=torch.float32, device=device)
+            handles = [None if t is None else symm.rendezvous(t, group) for t in (hi, lo, n2)]   # collective
+            self.sets.append({"bufs": (hi, lo, n2), "handles": handles, "peers": {}})
+        self.step = 0
         self.side = torch.cuda.Stream(device=device)
 
-    def start(self, hi: torch.Tensor, lo: Optional[torch.Tensor], n2: torch.Tensor, bounds: Sequence[Tuple[int, int]], P: int,
-              need_rank: Sequence[int], rank: int, world: int):
-        """Returns ((hi_buf, lo_buf, n2_buf), [(source rank, [request]), ...]) like distributed.start_shard_pipeline."""
+    def local_slices(self, row_a: int, row_b: int):
+        """This step's (hi, lo, n2) slices for rows [row_a, row_b): the embed kernel writes into them."""
+        hi, lo, n2 = self.sets[self.step & 1]["bufs"]
+        return hi[row_a:row_b], None if lo is None else lo[row_a:row_b], n2[row_a:row_b]
+
+    def _peer(self, cur, which: int, src: int):
+        key = (which, src)
+        if key not in cur["peers"]:
+            buf = cur["bufs"][which]
+            cur["peers"][key] = cur["handles"][which].get_buffer(src, tuple(buf.shape), buf.dtype)
+        return cur["peers"][key]
+
+    def publish_and_pull(self, bounds: Sequence[Tuple[int, int]], P: int, need_rank: Sequence[int], rank: int, world: int):
+        """After the local slices were written on the current stream: barrier, then pull the shards of `need_rank`.
+        Returns ((hi_buf, lo_buf, n2_buf), [(source rank, [request]), ...]) in arrival (ring) order."""
+        cur = self.sets[self.step & 1]
+        self.step += 1
         main = torch.cuda.current_stream()
-        h0 = self.handles[0]
-        a, b = bounds[rank]
-        h0.barrier(channel=0)
-        for buf, t in ((self.hi, hi), (self.lo, lo), (self.n2, n2)):
-            if buf is not None:
-                buf[a * P : b * P].copy_(t)
-        h0.barrier(channel=1)
+        cur["handles"][0].barrier(channel=0)              # stream-ordered: every rank's slice of this set is written
         self.side.wait_stream(main)
         steps: List[Tuple[int, list]] = []
         with torch.cuda.stream(self.side):
@@ -78,12 +91,14 @@ class SymmetricBank:
                 if src not in need_rank:
                     continue
                 sa, sb = bounds[src]
-                for buf, hdl in zip((self.hi, self.lo, self.n2), self.handles):
+                if sb <= sa:
+                    continue
+                for which, buf in enumerate(cur["bufs"]):
                     if buf is None:
                         continue
-                    peer = hdl.get_buffer(src, tuple(buf.shape), buf.dtype)
+                    peer = self._peer(cur, which, src)
                     buf[sa * P : sb * P].copy_(peer[sa * P : sb * P], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.side)
                 steps.append((src, [_EventRequest(ev)]))
-        return (self.hi, self.lo, self.n2), steps
+        return cur["bufs"], steps

@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round 2, GPU call 5 (one B200): fused single-pass embed -- tests, tuning sweep, bench, ncu.
+OUT=gpurun_out/r02_call5
+mkdir -p $OUT
+timeout 600 python -m pytest tests -m gpu -q -x --ignore=tests/test_gpu_baseline_sizes.py > $OUT/pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -15 $OUT/pytest_gpu.log
+timeout 300 python scripts/tune_embed_fused.py 100 > $OUT/tune_embed_fused.log 2>&1; echo "tune rc=$?"; cat $OUT/tune_embed_fused.log
+timeout 1500 python -m pytest tests/test_gpu_baseline_sizes.py -q > $OUT/pytest_baseline_sizes.log 2>&1; echo "baseline-size tests rc=$?"; tail -6 $OUT/pytest_baseline_sizes.log
+for spec in "config2" "config2 --keep-z" "config1" "config5 --cpu-sample 1 --steps 5"; do
+  name=$(echo $spec | tr ' ' '_' | tr -d '-')
+  timeout 300 python bench.py --workload $spec --warmup 3 > $OUT/bench_$name.json 2> $OUT/bench_$name.err; echo "bench $spec rc=$?"; tail -3 $OUT/bench_$name.err
+  python - "$OUT/bench_$name.json" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print("  images/s %.0f  ms/step %.3f  e2e %.0f  parity_ok %s  launches/step %.1f  stages %s  roofline frac %.3f (%.0f TF/s)" % (
+        d["value"], d["ms_per_step"], (d.get("e2e") or {}).get("value", 0), d.get("parity_ok"), d["gpu_launches"] / d["steps"],
+        {k: (round(v, 3) if isinstance(v, float) else v) for k, v in d["stages"].items() if k != "comm_ms_per_step_rank0"},
+        d["roofline"]["frac"], d["roofline"]["achieved"]))
+except Exception as e:
+    print("  no result:", e)
+PY
+done
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:embed_fused -s 4 -c 1 -o $OUT/r02_embed_fused \
+  python bench.py --workload config2 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_embed.log 2>&1; echo "ncu embed rc=$?"
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 60 --csv --log-file $OUT/launches.csv python bench.py --workload config2 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/launches.log 2>&1; echo "launch list rc=$?"
+ls -la $OUT

@@ -165,7 +165,7 @@ def test_cli_flow_with_stubbed_device_calls(tmp_path, monkeypatch):
         return out
 
     monkeypatch.setattr(main, "_device", lambda: torch.device("cpu"))
-    monkeypatch.setattr(main.backbones, "load", lambda name: torch.nn.Identity())
+    monkeypatch.setattr(main.backbones, "load", lambda name, **kw: torch.nn.Identity())
     monkeypatch.setattr(driver, "make_category_data", fake_make)
     monkeypatch.setattr(ops, "pairwise_l2", lambda X: torch.cdist(X.double(), X.double()).float())
     out = str(tmp_path / "outputs")
@@ -175,12 +175,12 @@ def test_cli_flow_with_stubbed_device_calls(tmp_path, monkeypatch):
     assert [(r[0], r[1]) for r in rows] == [("bottle", 0.5), ("bottle", 2.0), ("screw", 0.5), ("screw", 2.0)]
     assert all(r[2:] == (1.0, 1.0, 1.0) for r in rows)
     assert seen["bottle"]["supervised"] == "unsupervised" and seen["bottle"]["tau"] == [0.5, 2.0]
-    mode_dir = os.path.join(out, "synthetic", "wideresnet50", "unsupervised")
+    mode_dir = os.path.join(out, "synthetic", "wideresnet50-randinit", "unsupervised")
     assert os.path.exists(os.path.join(mode_dir, "layer2_layer3_16_16_2.0_1.0", "matrix_alpha_X_screw_unsupervised.pickle"))
     assert os.path.exists(os.path.join(out, "synthetic", "info", "info_bottle.pickle"))
     _, blocks = io.read_result_csv(os.path.join(mode_dir, "layer2_layer3_16_16_tau_result.csv"))
     assert [b[0] for b in blocks] == ["0.5", "2"] and [r[0] for r in blocks[1][1]] == ["bottle", "screw"]
     # ... and the offline evaluator (test.py's loop) reads the same tree back
-    ev = cluster.evaluate_runs(out, "synthetic", "wideresnet50", "unsupervised", ["layer2", "layer3"], 16, 16, [0.5, 2.0],
+    ev = cluster.evaluate_runs(out, "synthetic", "wideresnet50-randinit", "unsupervised", ["layer2", "layer3"], 16, 16, [0.5, 2.0],
                                objects=["bottle", "screw"], textures=[], dmat_fn=_cpu_dmat, write_csv=False)
     assert [r[0] for r in ev[0][1]] == ["bottle", "screw", "MVTec(object)"] and ev[0][1][2][1:] == (1.0, 1.0, 1.0)

@@ -24,7 +24,7 @@ def _images(n, seed=0, size=224):
 def test_anomaly_clustering_core_wideresnet50_matches_oracle():
     """BASELINE config 1 pipeline: WRN50 layer2+layer3 hooks -> _embed (1024 -> 1024) -> Matrix_Alpha."""
     dev = torch.device("cuda")
-    net = backbones.load("wideresnet50")
+    net = backbones.load("wideresnet50", allow_random_init=True)
     core = patchcore.AnomalyClusteringCore(dev).load(
         backbone=net, layers_to_extract_from=["layer2", "layer3"], device=dev, input_shape=(3, 224, 224),
         pretrain_embed_dimension=1024, target_embed_dimension=1024, patchsize=3)
@@ -74,13 +74,17 @@ def test_mirror_modules_standalone():
 def test_make_category_data_vit_writes_reference_pickle(tmp_path):
     """DINO ViT-S/8 shape (random init): driver == oracle, tau list from one pass, pickle layout."""
     dev = torch.device("cuda")
-    net = backbones.load("dino_vitsmall8")
+    net = backbones.load("dino_vitsmall8", allow_random_init=True)
     imgs = _images(4, seed=3)
     loader = [{"image": imgs[i:i + 1], "is_anomaly": torch.tensor([i % 2])} for i in range(4)]   # batch_size=1 like main.py:211
     layers = ["blocks.10", "blocks.11"]
     res = driver.make_category_data(None, "bottle", 512, 1024, ["dino_vitsmall8"], layers, 3, str(tmp_path), tau=[1.0, 2.0],
-                                    supervised="unsupervised", test_dataloader=loader, backbone=net, device=dev)
+                                    supervised="unsupervised", test_dataloader=loader, backbone=net, device=dev, allow_random_init=True)
     assert len(res) == 2
+    with pytest.raises(ValueError):      # a random-init stand-in is never accepted silently (nor is a missing backbone)
+        driver.make_category_data(None, "bottle", 512, 1024, ["dino_vitsmall8"], layers, 3, None, test_dataloader=loader, backbone=net)
+    with pytest.raises(ValueError):
+        driver.make_category_data(None, "bottle", 512, 1024, ["dino_vitsmall8"], layers, 3, None, test_dataloader=loader)
     agg = common.NetworkFeatureAggregator(net, layers, dev)
     feats = [agg(imgs.to(dev))[l].float().cpu() for l in layers]
     assert feats[0].shape == (4, 785, 384)
@@ -104,15 +108,19 @@ def test_cli_synthetic_run(tmp_path):
                      "--pretrain_embed_dimension", "1024", "--target_embed_dimension", "1024", "--tau", "1", "2",
                      "--synthetic_images", "8", "--synthetic_classes", "2", "--output_dir", str(tmp_path)])
     assert len(rows) == 2 and all(0.0 <= r[2] <= 1.0 for r in rows)
-    p = tmp_path / "synthetic" / "wideresnet50" / "unsupervised" / "layer2_layer3_1024_1024_2.0_1.0" / "matrix_alpha_X_bottle_unsupervised.pickle"
+    p = (tmp_path / "synthetic" / "wideresnet50-randinit" / "unsupervised" / "layer2_layer3_1024_1024_2.0_1.0"
+         / "matrix_alpha_X_bottle_unsupervised.pickle")
     assert os.path.exists(p)
+    # each per-tau pickle holds only its own alpha (a view of the [T,N,P] tensor would serialise every tau's storage)
+    a, X = io.load_matrix_alpha_X(str(p))
+    assert a.untyped_storage().nbytes() == a.numel() * 4 and not a.is_cuda
 
 
 def test_embed_over_dataloader_reference_convention():
     """AnomalyClusteringCore.embed(DataLoader, supervised) -> (list of per-batch row lists, list of is_anomaly)
     exactly as examples/main.py:266-267 consumes it: torch.tensor(Z) -> [N, P, D]."""
     dev = torch.device("cuda")
-    net = backbones.load("dino_vitsmall8")
+    net = backbones.load("dino_vitsmall8", allow_random_init=True)
     core = patchcore.AnomalyClusteringCore(dev).load(net, ["blocks.10", "blocks.11"], dev, (3, 224, 224), 256, 512, patchsize=3)
     imgs = _images(3, seed=5)
 
