@@ -782,33 +782,46 @@ __device__ __forceinline__ float store_operand_norm(void* Zhi, void* Zlo, long l
   return nv;
 }
 
+// Consumer threads of the fused kernel.  One thread owns TWO consecutive periods and keeps their values as float2
+// pairs, so that every add / fma of the pooling runs as ONE packed fp32x2 instruction (add.f32x2 / fma.rn.f32x2, new
+// on sm_100) for both periods: the kernel is instruction-issue bound (ncu, round 2: issue slots 77 % busy at a DRAM
+// throughput of 47 %), and this halves its arithmetic instructions.
+static constexpr int kFT = 128;
+static constexpr int kPP = 2;            // periods per thread
+
+__device__ __forceinline__ void consumer_bar_f() { asm volatile("bar.sync 1, %0;" ::"n"(kFT) : "memory"); }
+
 template <int A, int B, int R>
-__global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __grid_constant__ FusedParams fp) {
+__global__ void __launch_bounds__(kFT + 32, 3) embed_fused_kernel(const __grid_constant__ FusedParams fp) {
   constexpr int K = 3;
   constexpr int CPP = A / (K * K);
   constexpr int NOUT = B / R;
-  constexpr int NCH = kThreads * CPP;
+  constexpr int TCH = kPP * CPP;                 // channels per thread
+  constexpr int NCH = kFT * TCH;                 // channels per ring row
   const EmbedParams& p = fp.e;
   extern __shared__ __align__(128) float smem_f[];
   float* ring = smem_f;                                    // [kRing][K][NCH]
-  float* s_nacc = smem_f + (size_t)kRing * K * NCH;        // [kMaxSeg][kThreads] per-thread share of the row norms
+  float* s_nacc = smem_f + (size_t)kRing * K * NCH;        // [kMaxSeg][kFT] per-thread share of the row norms
   __shared__ __align__(8) uint64_t s_full[kRing], s_empty[kRing];
-  __shared__ float s_red[2][kThreads / 32];
+  __shared__ float s_red[2][kFT / 32];
   __shared__ float s_mu[kMaxLayers], s_rs[kMaxLayers];
   __shared__ long long s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool producer = (warp == kThreads / 32);
+  const bool producer = (warp == kFT / 32);
   if (tid == 0) {
     for (int i = 0; i < kRing; ++i) {
       e_mbar_init(e_smem_u32(&s_full[i]), 1);
-      e_mbar_init(e_smem_u32(&s_empty[i]), kThreads / 32);
+      e_mbar_init(e_smem_u32(&s_empty[i]), kFT / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint32_t jc = 0;                                         // ring column counter: identical sequence in both roles
+  uint32_t slot = 0, ph = 0;                               // ring position: identical sequence in both roles
+  const uint32_t full0 = e_smem_u32(&s_full[0]), empty0 = e_smem_u32(&s_empty[0]);
   const bool vec8 = (NOUT % 8 == 0) && (((p.ldz | fp.t_stride) & 7) == 0);
   const bool vec4 = (NOUT % 4 == 0) && (((p.ldz | fp.t_stride) & 3) == 0);
+  const bool f16 = (p.op_dtype == AC_DT_F16);
+  const float* ring_t = ring + tid * TCH;
 
   for (;;) {
     if (tid == 0) s_item = (long long)atomicAdd(fp.counter, 1u);
@@ -833,14 +846,14 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __g
               const int c_start = cx * NCH;
               const uint32_t bytes = (uint32_t)min(NCH, ly.C - c_start) * 4u;
               const float* src = ly.ptr + (long long)(p.b0 + bA) * ly.sb + c_start + (long long)y * ly.sh + (long long)xa * ly.sw;
-              for (int t = 0; t < nA; ++t, ++jc) {
-                const uint32_t slot = jc % kRing, ph = (jc / kRing) & 1u;
-                e_mbar_wait(e_smem_u32(&s_empty[slot]), ph ^ 1u);
+              for (int t = 0; t < nA; ++t) {
+                e_mbar_wait(empty0 + slot * 8, ph ^ 1u);
                 const int ntok = min(K, npos - K * t);
-                const uint32_t fb = e_smem_u32(&s_full[slot]);
+                const uint32_t fb = full0 + slot * 8;
                 e_mbar_expect_tx(fb, (uint32_t)ntok * bytes);
                 for (int ki = 0; ki < ntok; ++ki)
                   e_bulk_g2s(e_smem_u32(ring + ((size_t)slot * K + ki) * NCH), src + (long long)(K * t + ki) * ly.sw, bytes, fb);
+                if (++slot == kRing) { slot = 0; ph ^= 1u; }
               }
             }
           }
@@ -852,9 +865,8 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __g
               const int c_start = cx * NCH;
               const uint32_t bytes = (uint32_t)min(NCH, ly.C - c_start) * 4u;
               const float* src = ly.ptr + (long long)(p.b0 + bE) * ly.sb + c_start;
-              for (int j = 0; j < ncols; ++j, ++jc) {
-                const uint32_t slot = jc % kRing, ph = (jc / kRing) & 1u;
-                e_mbar_wait(e_smem_u32(&s_empty[slot]), ph ^ 1u);
+              for (int j = 0; j < ncols; ++j) {
+                e_mbar_wait(empty0 + slot * 8, ph ^ 1u);
                 const int ix = xa - p.pad + j;
                 const bool cin = (ix >= 0) && (ix < ly.W);
                 uint32_t nrows = 0;
@@ -863,7 +875,7 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __g
                   const int iy = y - p.pad + ki;
                   nrows += (cin && iy >= 0 && iy < ly.H) ? 1u : 0u;
                 }
-                const uint32_t fb = e_smem_u32(&s_full[slot]);
+                const uint32_t fb = full0 + slot * 8;
                 if (nrows == 0) {
                   e_mbar_arrive(fb);
                 } else {
@@ -875,48 +887,48 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __g
                       e_bulk_g2s(e_smem_u32(ring + ((size_t)slot * K + ki) * NCH), src + (long long)iy * ly.sh + (long long)ix * ly.sw, bytes, fb);
                   }
                 }
+                if (++slot == kRing) { slot = 0; ph ^= 1u; }
               }
             }
           }
         }
       }
     } else {
-      // ================================================================ consumers (kThreads)
+      // ================================================================ consumers (kFT)
       // ---- phase A: this item's share of the LayerNorm statistics of image bA
       if (bA >= 0 && p.layernorm) {
         for (int l = 0; l < p.L; ++l) {
           float s = 0.f, qq = 0.f;
           for (int cx = 0; cx < fp.gx; ++cx) {
-            const bool active = (cx * kThreads + tid) < fp.nperiods;
-            for (int t = 0; t < nA; ++t, ++jc) {
-              const uint32_t slot = jc % kRing, ph = (jc / kRing) & 1u;
-              e_mbar_wait(e_smem_u32(&s_full[slot]), ph);
+            const int m0 = (cx * kFT + tid) * kPP;            // first period of this thread
+            for (int t = 0; t < nA; ++t) {
+              e_mbar_wait(full0 + slot * 8, ph);
               const int ntok = min(K, npos - K * t);
-              if (active) {
-                const float* col = ring + (size_t)slot * K * NCH + tid * CPP;
+              const float* col = ring_t + (size_t)slot * K * NCH;
 #pragma unroll
-                for (int ki = 0; ki < K; ++ki)
-                  if (ki < ntok) {
+              for (int ki = 0; ki < K; ++ki)
+                if (ki < ntok) {
 #pragma unroll
-                    for (int c = 0; c < CPP; ++c) { const float v = col[ki * NCH + c]; s += v; qq = fmaf(v, v, qq); }
-                  }
-              }
+                  for (int c = 0; c < TCH; ++c)
+                    if (m0 + c / CPP < fp.nperiods) { const float v = col[ki * NCH + c]; s += v; qq = fmaf(v, v, qq); }
+                }
               __syncwarp();
-              if (lane == 0) e_mbar_arrive(e_smem_u32(&s_empty[slot]));
+              if (lane == 0) e_mbar_arrive(empty0 + slot * 8);
+              if (++slot == kRing) { slot = 0; ph ^= 1u; }
             }
           }
           s = warp_sum(s);
           qq = warp_sum(qq);
           if (lane == 0) { s_red[0][warp] = s; s_red[1][warp] = qq; }
-          consumer_bar();
+          consumer_bar_f();
           if (tid == 0) {
             double a = 0, c2 = 0;
-            for (int w = 0; w < kThreads / 32; ++w) { a += (double)s_red[0][w]; c2 += (double)s_red[1][w]; }
+            for (int w = 0; w < kFT / 32; ++w) { a += (double)s_red[0][w]; c2 += (double)s_red[1][w]; }
             double* o = fp.stats + (((long long)bA * p.L + l) * fp.S + sg) * 2;
             o[0] = a;
             o[1] = c2;
           }
-          consumer_bar();
+          consumer_bar_f();
         }
         if (tid == 0) {
           __threadfence();
@@ -933,7 +945,7 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __g
               if (clock64() - t0 > 4000000000LL) __trap();     // a broken schedule must fail the launch, never hang the GPU
             }
           }
-          consumer_bar();
+          consumer_bar_f();
           if (warp == 0) {
             for (int l = 0; l < p.L; ++l) {
               const double* st = fp.stats + (((long long)bE * p.L + l) * fp.S) * 2;
@@ -948,14 +960,14 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __g
               if (lane == 0) { s_mu[l] = (float)m; s_rs[l] = (float)(1.0 / sqrt(var + (double)p.eps)); }
             }
           }
-          consumer_bar();
+          consumer_bar_f();
         }
         const long long row0 = ((long long)(p.b0 + bE) * p.h0 + y) * p.w0;
         bool first = true;
         for (int l = 0; l < p.L; ++l) {
           const LayerDev& ly = p.layers[l];
           const float mu = p.layernorm ? s_mu[l] : 0.f, rs = p.layernorm ? s_rs[l] : 1.f;
-          const float nmr = -mu * rs;
+          const float2 mu2 = make_float2(mu, mu), nmr2 = make_float2(-mu * rs, -mu * rs);
           bool rowok[K];
 #pragma unroll
           for (int ki = 0; ki < K; ++ki) {
@@ -963,77 +975,95 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __g
             rowok[ki] = (iy >= 0) && (iy < ly.H);
           }
           for (int cx = 0; cx < fp.gx; ++cx, first = false) {
-            const int m = cx * kThreads + tid;
-            const bool active = m < fp.nperiods;
-            const int t0 = l * fp.t_stride + (active ? m : 0) * NOUT;
-            float v[CPP][K][K];   // [channel][ki][physical column slot]; out-of-map taps hold mu (= 0 after the LayerNorm)
+            const int m0 = (cx * kFT + tid) * kPP;
+            const bool actA = m0 < fp.nperiods, actB = m0 + 1 < fp.nperiods;
+            // the two periods' outputs are adjacent: [t0, t0 + NOUT) and [t0 + NOUT, t0 + 2 NOUT)
+            long long idx = (row0 + xa) * p.ldz + (long long)l * fp.t_stride + (long long)(actA ? m0 : 0) * NOUT;
+            float2 v[CPP][K][K];   // [channel][ki][physical column slot], .x = first period, .y = second; out-of-map taps hold mu
 #pragma unroll
             for (int c = 0; c < CPP; ++c)
 #pragma unroll
               for (int ki = 0; ki < K; ++ki)
 #pragma unroll
-                for (int kj = 0; kj < K; ++kj) v[c][ki][kj] = mu;
+                for (int kj = 0; kj < K; ++kj) v[c][ki][kj] = mu2;
+            float* na = s_nacc + tid;
             auto step = [&](auto rot_tag, int j) {
               constexpr int ROT = decltype(rot_tag)::value;
               constexpr int SLOT = (ROT + K - 1) % K;
-              const uint32_t slot = jc % kRing, ph = (jc / kRing) & 1u;
-              ++jc;
               const int ix = xa - p.pad + j;
               const bool cin = (ix >= 0) && (ix < ly.W);
-              e_mbar_wait(e_smem_u32(&s_full[slot]), ph);
-              const float* col = ring + (size_t)slot * K * NCH + tid * CPP;
+              e_mbar_wait(full0 + slot * 8, ph);
+              const float* col = ring_t + (size_t)slot * K * NCH;
 #pragma unroll
               for (int ki = 0; ki < K; ++ki) {
                 if (cin && rowok[ki]) {                      // warp-uniform
 #pragma unroll
-                  for (int c = 0; c < CPP; ++c) v[c][ki][SLOT] = col[ki * NCH + c];
+                  for (int c = 0; c < CPP; ++c) v[c][ki][SLOT] = make_float2(col[ki * NCH + c], col[ki * NCH + CPP + c]);
                 } else {
 #pragma unroll
-                  for (int c = 0; c < CPP; ++c) v[c][ki][SLOT] = mu;
+                  for (int c = 0; c < CPP; ++c) v[c][ki][SLOT] = mu2;
                 }
               }
               __syncwarp();
-              if (lane == 0) e_mbar_arrive(e_smem_u32(&s_empty[slot]));
-              const int x = xa + j - (K - 1);
-              if (x < xa) return;
+              if (lane == 0) e_mbar_arrive(empty0 + slot * 8);
+              if (++slot == kRing) { slot = 0; ph ^= 1u; }
+              if (j < K - 1) return;                         // the window is not full yet
               float nv = 0.f;
-              if (active) {
-                float out[NOUT];
+              if (actA) {
+                float2 out[NOUT];
 #pragma unroll
                 for (int o = 0; o < NOUT; ++o) {
-                  float acc_o = nmr;
+                  float2 acc_o = nmr2;
 #pragma unroll
                   for (int jj = 0; jj < R; ++jj) {
                     const int r = o * R + jj;
                     const int f0 = (r * A) / B, f1 = ((r + 1) * A + B - 1) / B;
-                    float sacc = 0.f;
+                    float2 sacc = v[f0 / (K * K)][(f0 % (K * K)) / K][((f0 % K) + ROT) % K];
 #pragma unroll
                     for (int f = 0; f < A; ++f)
-                      if (f >= f0 && f < f1) sacc += v[f / (K * K)][(f % (K * K)) / K][((f % K) + ROT) % K];
-                    acc_o = fmaf(sacc, rs * (1.0f / (float)(R * (f1 - f0))), acc_o);
+                      if (f > f0 && f < f1) sacc = __fadd2_rn(sacc, v[f / (K * K)][(f % (K * K)) / K][((f % K) + ROT) % K]);
+                    const float cf = rs * (1.0f / (float)(R * (f1 - f0)));
+                    acc_o = __ffma2_rn(sacc, make_float2(cf, cf), acc_o);
                   }
                   out[o] = acc_o;
                 }
-                const long long idx = (row0 + x) * p.ldz + t0;
+                float oa[NOUT], ob[NOUT];
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) { oa[o] = out[o].x; ob[o] = out[o].y; }
                 if (p.Z) {
                   if (vec4) {
 #pragma unroll
                     for (int o = 0; o + 4 <= NOUT; o += 4)
-                      *reinterpret_cast<float4*>(p.Z + idx + o) = make_float4(out[o], out[o + 1], out[o + 2], out[o + 3]);
+                      *reinterpret_cast<float4*>(p.Z + idx + o) = make_float4(oa[o], oa[o + 1], oa[o + 2], oa[o + 3]);
+                    if (actB) {
+#pragma unroll
+                      for (int o = 0; o + 4 <= NOUT; o += 4)
+                        *reinterpret_cast<float4*>(p.Z + idx + NOUT + o) = make_float4(ob[o], ob[o + 1], ob[o + 2], ob[o + 3]);
+                    }
                   } else {
 #pragma unroll
-                    for (int o = 0; o < NOUT; ++o) p.Z[idx + o] = out[o];
+                    for (int o = 0; o < NOUT; ++o) p.Z[idx + o] = oa[o];
+                    if (actB) {
+#pragma unroll
+                      for (int o = 0; o < NOUT; ++o) p.Z[idx + NOUT + o] = ob[o];
+                    }
                   }
                 }
                 if (p.Zhi) {
-                  if (p.op_dtype == AC_DT_F16) nv = store_operand_norm<__half, NOUT>(p.Zhi, p.Zlo, idx, vec8, out);
-                  else nv = store_operand_norm<__nv_bfloat16, NOUT>(p.Zhi, p.Zlo, idx, vec8, out);
+                  if (f16) {
+                    nv = store_operand_norm<__half, NOUT>(p.Zhi, p.Zlo, idx, vec8, oa);
+                    if (actB) nv += store_operand_norm<__half, NOUT>(p.Zhi, p.Zlo, idx + NOUT, vec8, ob);
+                  } else {
+                    nv = store_operand_norm<__nv_bfloat16, NOUT>(p.Zhi, p.Zlo, idx, vec8, oa);
+                    if (actB) nv += store_operand_norm<__nv_bfloat16, NOUT>(p.Zhi, p.Zlo, idx + NOUT, vec8, ob);
+                  }
                 }
               }
               if (fp.n2) {
-                float* na = s_nacc + (x - xa) * kThreads + tid;
                 *na = first ? nv : (*na + nv);
+                na += kFT;
               }
+              idx += p.ldz;
             };
             for (int j0 = 0; j0 < ncols; j0 += 3) {
               step(std::integral_constant<int, 1>{}, j0);
@@ -1044,11 +1074,11 @@ __global__ void __launch_bounds__(kThreads + 32, 3) embed_fused_kernel(const __g
         }
         if (fp.n2) {
           // squared norms of the operand rows of this segment: fixed summation order (bit-reproducible)
-          consumer_bar();
-          for (int pos = warp; pos < npos; pos += kThreads / 32) {
+          consumer_bar_f();
+          for (int pos = warp; pos < npos; pos += kFT / 32) {
             float a = 0.f;
 #pragma unroll
-            for (int k2 = 0; k2 < kThreads / 32; ++k2) a += s_nacc[pos * kThreads + lane + 32 * k2];
+            for (int k2 = 0; k2 < kFT / 32; ++k2) a += s_nacc[pos * kFT + lane + 32 * k2];
             a = warp_sum(a);
             if (lane == 0) fp.n2[row0 + xa + pos] = a;
           }
@@ -1560,7 +1590,7 @@ static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, 
   fp.S = p.h0 * p.nxseg;
   fp.LA = std::max(1, std::min(g_fused_la, p.B));
   fp.nperiods = pr.nperiods;
-  fp.gx = ceil_div(pr.nperiods, kThreads);
+  fp.gx = ceil_div(pr.nperiods, kFT * kPP);
   fp.t_stride = pr.ncols;
   fp.n_items = (long long)(p.B + fp.LA) * fp.S;
   const size_t stats_b = ((size_t)p.B * p.L * fp.S * 2 * sizeof(double) + 255) & ~(size_t)255;
@@ -1574,9 +1604,9 @@ static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, 
 #define X(a, b, r)                                                                                                   \
   if (pr.A == a && pr.B == b && pr.R == r) {                                                                         \
     auto kern = embed_fused_kernel<a, b, r>;                                                                         \
-    const size_t smem = ((size_t)kRing * 3 * kThreads * (a / 9) + (size_t)kMaxSeg * kThreads) * sizeof(float);       \
+    const size_t smem = ((size_t)kRing * 3 * kFT * kPP * (a / 9) + (size_t)kMaxSeg * kFT) * sizeof(float);           \
     AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
-    kern<<<grid, kThreads + 32, smem, st>>>(fp);                                                                     \
+    kern<<<grid, kFT + 32, smem, st>>>(fp);                                                                          \
     AC_LAUNCH_CHECK();                                                                                               \
     return AC_OK;                                                                                                    \
   }
@@ -1690,6 +1720,9 @@ extern "C" int ac_embed_ex(const ac_layer_t* layers, int L, int B, int patchsize
   rc = get_plan(layers, L, patchsize, stride, Dp, D, layernorm, eps, plan_sp);
   if (rc) return rc;
   const Plan& plan = *plan_sp;
+  // operand-only output needs the fused aggregator (no Aggregator window straddling two layers): refuse BEFORE anything is
+  // enqueued -- callers ask for Z as well in that case (pipeline.embed_images does)
+  if (!plan.fused && !Z) return AC_ERR_UNSUPPORTED;
   EmbedParams p = plan.p;   // cached geometry; pointers and batch are per call
   p.eps = eps;
   for (int l = 0; l < L; ++l) {

@@ -60,6 +60,18 @@ def patch_grid(H: int, W: int, patchsize: int, stride: int) -> Tuple[int, int]:
     return ((H + 2 * pad - (patchsize - 1) - 1) // stride + 1, (W + 2 * pad - (patchsize - 1) - 1) // stride + 1)
 
 
+def aggregator_fusable(n_layers: int, pretrain_dim: int, target_dim: int) -> bool:
+    """True when no Aggregator window (adaptive_avg_pool1d of the L*Dp concat to D, common.py:181-183) straddles two layers:
+    only then can ac_embed write the tensor-core operands without the fp32 Z (same rule as csrc/embed.cu)."""
+    agg_in = n_layers * pretrain_dim
+    for t in range(target_dim):
+        g0 = (t * agg_in) // target_dim
+        g1 = ((t + 1) * agg_in + target_dim - 1) // target_dim
+        if g0 // pretrain_dim != (g1 - 1) // pretrain_dim:
+            return False
+    return True
+
+
 def make_groups(sizes: Sequence[int], device) -> torch.Tensor:
     """Category table of the _ex entry points: int32 [sum(sizes), 2] = (first image, image count) of the category of every
     image, for categories stored back to back (per-category banks, examples/main.py:353)."""

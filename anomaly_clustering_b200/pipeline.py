@@ -13,6 +13,7 @@ patchcore.py:358-361 + main.py:267) and one min-distance pass serves every tau.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -48,6 +49,11 @@ def resolve_precision(precision: str, taus: Sequence[float]) -> str:
         return precision
     small = [t for t in taus if abs(float(t)) < AUTO_REFINE_BELOW_TAU]
     return "f16r" if small else "f16"
+
+
+@functools.lru_cache(maxsize=64)
+def _fusable(n_layers: int, pretrain_dim: int, target_dim: int) -> bool:
+    return ops.aggregator_fusable(n_layers, pretrain_dim, target_dim)
 
 
 _OPERAND_OF = {"f16": ("f16", False), "bf16": ("bf16", False), "f16x3": ("f16", True), "bf16x3": ("bf16", True), "f32": (None, False),
@@ -103,7 +109,8 @@ def embed_images(
     h, w = ops.patch_grid(views[0].shape[2], views[0].shape[3], patchsize, stride)
     P = h * w
     dev = views[0].device
-    need_z = want_z or operand is None
+    # operand-only output needs Aggregator windows that stay inside one layer; otherwise Z is produced (and dropped below)
+    need_z = want_z or operand is None or not _fusable(len(views), pretrain_dim, target_dim)
     Z = torch.empty(N * P, target_dim, dtype=torch.float32, device=dev) if need_z else None
     hi = lo = n2 = None
     if operand is not None:
@@ -127,6 +134,8 @@ def embed_images(
             out_n2=None if n2 is None else n2[sl],
         )
     _mark("embed_end")
+    if not (want_z or operand is None):
+        Z = None
     return PatchSet(n_img=N, P=P, D=target_dim, grid=(h, w), Z=Z, hi=hi, lo=lo, n2=n2)
 
 

@@ -562,3 +562,19 @@ def test_batched_categories_config2_width_straddling_blocks():
         ref = pipeline.run_path([x[start:start + n] for x in f], 3, 1, 2048, 4096, "unsupervised", [1.0], precision="f16", keep_z=False)
         assert torch.equal(got[c].w, ref.w) and torch.equal(got[c].Dmat, ref.Dmat), c
         start += n
+
+
+def test_supervised_with_straddling_aggregator_windows():
+    """L = 3 layers, Dp = 32, D = 64: Aggregator windows straddle layers, so the operands cannot be written without Z.
+    The supervised bank (embedded without Z) must still work (it used to fail with AC_ERR_UNSUPPORTED)."""
+    gen = torch.Generator().manual_seed(9)
+    feats = [torch.randn(4, 8, 6, 6, generator=gen) for _ in range(3)]
+    bank = [torch.randn(3, 8, 6, 6, generator=gen) for _ in range(3)]
+    assert not ops.aggregator_fusable(3, 32, 64)
+    want = restated.full_path(feats, 3, 1, 32, 64, 2.0, "supervised", bank_features=bank)
+    res = pipeline.run_path([f.cuda() for f in feats], 3, 1, 32, 64, "supervised", [2.0], bank_features=[f.cuda() for f in bank],
+                            precision="f16")
+    assert (res.alpha64[0].cpu() - want[2]).abs().max().item() <= 1e-3
+    assert rel_l2(res.X[0].cpu().numpy(), want[3]) <= 1e-3
+    with pytest.raises(Exception):       # the C entry point refuses before enqueuing anything
+        ops.embed([f.cuda() for f in bank], 3, 1, 32, 64, want_z=False, operand="f16")
