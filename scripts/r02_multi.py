@@ -48,11 +48,13 @@ for n_img, layers, Dp, D in ((13, [(96, 12, 12, True), (96, 12, 12, True)], 256,
     lo, hi = bounds[rank]
     feats, _ = synth.planted_features_device(range(lo, hi), layers, device="cuda")
     allf = synth.planted_features_device(range(n_img), layers, device="cuda")[0] if rank == 0 else None
-    for name, env, prec, taus in (("default", {}, "f16", [1.0, 2.0]), ("pipeline", {"AC_SHARD_PIPELINE": "1"}, "f16", [1.0, 2.0]),
+    for name, env, prec, taus in (("default (symm)", {}, "f16", [1.0, 2.0]), ("nccl", {"AC_SHARD_TRANSPORT": "nccl"}, "f16", [1.0, 2.0]),
+                                  ("nccl pipeline", {"AC_SHARD_TRANSPORT": "nccl", "AC_SHARD_PIPELINE": "1"}, "f16", [1.0, 2.0]),
                                   ("all-pairs", {"SYM": "0"}, "f16", [1.0]), ("refined f16r", {}, "auto", [0.1, 1.0])):
-        if name == "pipeline" and world <= 2:
+        if name == "nccl pipeline" and world <= 2:
             continue
         os.environ["AC_SHARD_PIPELINE"] = env.get("AC_SHARD_PIPELINE", "0")
+        os.environ["AC_SHARD_TRANSPORT"] = env.get("AC_SHARD_TRANSPORT", "symm")
         try:
             a64, X, Dm, w = distributed.run_path_sharded(feats, n_img, 3, 1, Dp, D, taus, precision=prec, symmetric=env.get("SYM") != "0")
             torch.cuda.synchronize()
@@ -72,11 +74,13 @@ for n_img, layers, Dp, D in ((13, [(96, 12, 12, True), (96, 12, 12, True)], 256,
         dist.barrier()
     del feats, allf
 os.environ["AC_SHARD_PIPELINE"] = "0"
+os.environ["AC_SHARD_TRANSPORT"] = "symm"
 torch.cuda.empty_cache()
 
 
 # ---------------------------------------------------------------- 2. bench lines
 def run_bench(tag, argv, env=None):
+    saved = {k: os.environ.get(k) for k in (env or {})}
     for k, v in (env or {}).items():
         os.environ[k] = v
     buf = io.StringIO()
@@ -86,8 +90,11 @@ def run_bench(tag, argv, env=None):
             bench.main(argv + ["--gpus", str(world)])
     except BaseException as e:  # noqa: BLE001
         log("bench %s FAILED: %r" % (tag, e))
-    for k in (env or {}):
-        os.environ[k] = "0"
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
     if rank == 0:
         line = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
         with open(os.path.join(OUT, "bench_%s_n%d.json" % (tag.replace(" ", "_"), world)), "w") as f:
@@ -105,11 +112,14 @@ def run_bench(tag, argv, env=None):
     dist.barrier()
 
 
-which = os.environ.get("AC_MULTI_WHICH", "c2,c2pipe,c2r,c3,c4,c4pc,c5,trace").split(",")
+which = os.environ.get("AC_MULTI_WHICH", "c2,c2nccl,c2r,c3,c4,c4pc,c5,trace").split(",")
 if "c2" in which:
     run_bench("config2 default", ["--workload", "config2", "--steps", "20", "--warmup", "5", "--no-cpu-baseline"])
+if "c2nccl" in which:
+    run_bench("config2 nccl", ["--workload", "config2", "--steps", "20", "--warmup", "5", "--no-e2e", "--no-cpu-baseline"], {"AC_SHARD_TRANSPORT": "nccl"})
 if "c2pipe" in which and world > 2:
-    run_bench("config2 pipeline", ["--workload", "config2", "--steps", "20", "--warmup", "5", "--no-e2e", "--no-cpu-baseline"], {"AC_SHARD_PIPELINE": "1"})
+    run_bench("config2 nccl pipeline", ["--workload", "config2", "--steps", "20", "--warmup", "5", "--no-e2e", "--no-cpu-baseline"],
+              {"AC_SHARD_TRANSPORT": "nccl", "AC_SHARD_PIPELINE": "1"})
 if "c2r" in which:
     run_bench("config2 f16r", ["--workload", "config2", "--steps", "10", "--warmup", "3", "--no-e2e", "--precision", "f16r"])
 if "c3" in which:
@@ -128,10 +138,8 @@ if "trace" in which:
     layers = [(768, 28, 28, True), (768, 28, 28, True)]
     lo, hi = distributed.shard_bounds(100, world)[rank]
     feats, _ = synth.planted_features_device(range(lo, hi), layers, device="cuda")
-    for name, pipe in (("default", "0"), ("pipeline", "1")):
-        if pipe == "1" and world <= 2:
-            continue
-        os.environ["AC_SHARD_PIPELINE"] = pipe
+    for name, transport in (("symm", "symm"), ("nccl", "nccl")):
+        os.environ["AC_SHARD_TRANSPORT"] = transport
         for _ in range(5):
             distributed.run_path_sharded(feats, 100, 3, 1, 2048, 4096, [1.0], precision="f16", keep_z=False)
         torch.cuda.synchronize()
@@ -152,7 +160,7 @@ if "trace" in which:
                 for e in gpu:
                     f.write("%10.1f us  +%8.1f us  stream %s  %s\n" % (e["ts"] - t0, e["dur"], e.get("args", {}).get("stream"), e["name"][:110]))
             os.remove(path)
-    os.environ["AC_SHARD_PIPELINE"] = "0"
+    os.environ["AC_SHARD_TRANSPORT"] = "symm"
 log("all checks %s" % ("OK" if ok_all else "HAD MISMATCHES"))
 dist.barrier()
 dist.destroy_process_group()
