@@ -735,6 +735,7 @@ struct FusedParams {
   unsigned int* counter;   // item claims
   int S, LA, nperiods, gx, t_stride;
   long long n_items;       // (B + LA) * S
+  const float* zero_row;   // >= 4 KB of zeros (lean kernel: stands in for taps outside the map)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -1086,6 +1087,363 @@ __global__ void __launch_bounds__(kFT + 32, 3) embed_fused_kernel(const __grid_c
       }
     }
     __syncthreads();      // s_item / s_nacc / s_red are reused by the next item
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lean form of the fused kernel for the shapes the headline workloads use (fp16 operands + norms, optionally fp32 Z,
+// every consumer thread active).  Same schedule, ring and arithmetic as embed_fused_kernel; what changes is the cost of a
+// step.  ncu of the general kernel (profiles/r02_ncu_full.md): 355 warp instructions per staged column of which ~100 do
+// the work -- the rest were per-value selects for taps outside the map, register moves that re-pair LDS.64 results for
+// the packed adds, run-time switches on the output set and generic-pointer shared-memory addressing.  Here
+//   * taps outside the map are staged as ZEROS by the producer (bulk copies from a zero row in the workspace), so the
+//     consumers load unconditionally; the zero-padding of the reference (pad AFTER the LayerNorm, patchcore.py:384-385 then
+//     :447) is restored on the few edge positions by adding mu * rstd * (missing taps / window) per output,
+//   * staged values are read with 32-bit ld.shared straight into the halves of the packed registers (immediate offsets
+//     from one base register per step),
+//   * the output set is a template parameter.
+__device__ __forceinline__ float2 e_lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float e_lds32(uint32_t base) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(base), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ void e_mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  while (!e_mbar_try(bar, parity)) {}
+}
+
+// one staged row of this thread: .x = channel c of its first period, .y = channel c of its second period, which lies
+// HALF floats further (periods tid and tid + FT): far enough apart that ptxas keeps the 32-bit loads apart and lets each
+// land in its half of the packed register pair (adjacent periods became LDS.64 + two moves per pair)
+template <int KI, int NCH_, int HALF>
+__device__ __forceinline__ void e_load_row3(uint32_t base, float2& a, float2& b, float2& c) {
+  a = make_float2(e_lds32<(KI * NCH_ + 0) * 4>(base), e_lds32<(KI * NCH_ + HALF + 0) * 4>(base));
+  b = make_float2(e_lds32<(KI * NCH_ + 1) * 4>(base), e_lds32<(KI * NCH_ + HALF + 1) * 4>(base));
+  c = make_float2(e_lds32<(KI * NCH_ + 2) * 4>(base), e_lds32<(KI * NCH_ + HALF + 2) * 4>(base));
+}
+
+static constexpr int kRingL = 7;         // ring depth of the lean kernel (72 KB of shared memory per CTA at 768 channels, 3 CTAs per SM)
+static constexpr int kItemQ = 2;         // items the producer may be ahead of the consumers
+
+template <int A, int B, int R, int FT, bool WZ>
+__global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast_kernel(const __grid_constant__ FusedParams fp) {
+  constexpr int K = 3;
+  constexpr int CPP = A / (K * K);
+  constexpr int NOUT = B / R;
+  constexpr int TCH = kPP * CPP;                 // channels per thread (two periods)
+  constexpr int NCH = FT * TCH;                  // channels per ring row == C of every layer (host checks)
+  static_assert(NOUT % 8 == 0 || NOUT == 4, "operand rows are written in 16-byte pieces");
+  static_assert(TCH % 2 == 0, "the statistics phase reads channel pairs");
+  static_assert(CPP == 3, "three channels per period (9C : Dp = 27 : B)");
+  const EmbedParams& p = fp.e;
+  extern __shared__ __align__(128) float smem_f[];
+  float* ring = smem_f;                                    // [kRingL][K][NCH]
+  float* s_nacc = smem_f + (size_t)kRingL * K * NCH;       // [kMaxSeg][FT] per-thread share of the row norms
+  __shared__ __align__(8) uint64_t s_full[kRingL], s_empty[kRingL];
+  __shared__ __align__(8) uint64_t s_qfull[kItemQ], s_qempty[kItemQ];
+  __shared__ long long s_items[kItemQ];
+  __shared__ float s_mu[kMaxLayers], s_rs[kMaxLayers];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = (warp == FT / 32);
+  if (tid == 0) {
+    for (int i = 0; i < kRingL; ++i) {
+      e_mbar_init(e_smem_u32(&s_full[i]), 1);
+      e_mbar_init(e_smem_u32(&s_empty[i]), FT / 32);
+    }
+    for (int i = 0; i < kItemQ; ++i) {
+      e_mbar_init(e_smem_u32(&s_qfull[i]), 1);
+      e_mbar_init(e_smem_u32(&s_qempty[i]), FT / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t slot = 0, ph = 0;                               // ring position: identical sequence in both roles
+  const uint32_t full0 = e_smem_u32(&s_full[0]), empty0 = e_smem_u32(&s_empty[0]);
+  const uint32_t ring_a = e_smem_u32(ring) + (uint32_t)tid * TCH * 4u;      // statistics phase: TCH consecutive channels of a ring row
+  const uint32_t ring_t = e_smem_u32(ring) + (uint32_t)tid * CPP * 4u;      // embed phase: periods tid and tid + FT
+  constexpr uint32_t kSlotBytes = (uint32_t)K * NCH * 4u;
+  constexpr uint32_t kRowBytes = (uint32_t)NCH * 4u;
+
+  // Items are claimed by the PRODUCER, which publishes them through a kItemQ-deep queue and keeps staging: the copies of
+  // the next item (its statistics slots come from DRAM) are in flight while the consumers still work on this one.  (With
+  // one CTA-wide claim per item the ring ran dry at every item boundary: 28 % of the consumers' cycles waited for data.)
+  // The earliest unfinished item is always at the head of its CTA's queue, so the wait of an embed phase for the
+  // statistics of its image cannot deadlock.
+  uint32_t qs = 0, qph = 0;
+  if (producer && lane != 0) return;
+  for (;;) {
+    long long item;
+    if (producer) {
+      e_mbar_wait(e_smem_u32(&s_qempty[qs]), qph ^ 1u);
+      item = (long long)atomicAdd(fp.counter, 1u);
+      s_items[qs] = item;
+      asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(e_smem_u32(&s_qfull[qs])) : "memory");
+    } else {
+      long long it = 0;
+      if (lane == 0) {
+        e_mbar_wait(e_smem_u32(&s_qfull[qs]), qph);
+        it = *reinterpret_cast<volatile long long*>(&s_items[qs]);
+        e_mbar_arrive(e_smem_u32(&s_qempty[qs]));
+      }
+      item = __shfl_sync(0xffffffffu, it, 0);
+    }
+    if (++qs == kItemQ) { qs = 0; qph ^= 1u; }
+    if (item >= fp.n_items) break;
+    const int q = (int)(item / fp.S), sg = (int)(item - (long long)q * fp.S);
+    const int y = sg / p.nxseg, xs = sg - y * p.nxseg;
+    const int xa = xs * p.xseg_len, xb = min(p.w0, xa + p.xseg_len), npos = xb - xa;
+    const int bA = (q < p.B) ? q : -1;                     // image whose statistics slice is reduced
+    const int bE = q - fp.LA;                              // image whose slice is embedded (< 0: prologue item)
+    const int nA = (npos + K - 1) / K;                     // statistics slots: K tokens each (missing ones staged as zeros)
+    const int ncols = npos + K - 1;                        // embed slots: input columns xa-1 .. xb
+
+    if (producer) {
+      // ================================================================ producer thread: every slot is K full rows
+      // statistics slots of image bA first (they never wait for anything), then the embed slots of image bE.  (Spreading the
+      // statistics slots through the embed loop hides their DRAM latency but delays done[bA] to the end of an item that
+      // itself waits for done[bE]: the images then advance LA per item time -- measured 2.5 / 1.3 / 0.65 ms at LA 1 / 2 / 4.)
+      const bool hasA = (bA >= 0) && p.layernorm, hasB = (bE >= 0);
+      if (hasA) {
+        for (int l = 0; l < p.L; ++l) {
+          const LayerDev& ly = p.layers[l];
+          const float* srcA = ly.ptr + (long long)bA * ly.sb + (long long)y * ly.sh + (long long)xa * ly.sw;
+          for (int t = 0; t < nA; ++t) {
+            e_mbar_wait(empty0 + slot * 8, ph ^ 1u);
+            const uint32_t fb = full0 + slot * 8;
+            e_mbar_expect_tx(fb, kSlotBytes);
+#pragma unroll
+            for (int ki = 0; ki < K; ++ki) {
+              const int tok = K * t + ki;
+              e_bulk_g2s(e_smem_u32(ring + ((size_t)slot * K + ki) * NCH), (tok < npos) ? srcA + (long long)tok * ly.sw : fp.zero_row,
+                         kRowBytes, fb);
+            }
+            if (++slot == kRingL) { slot = 0; ph ^= 1u; }
+          }
+        }
+      }
+      if (hasB) {
+        for (int l = 0; l < p.L; ++l) {
+          const LayerDev& ly = p.layers[l];
+          const float* src = ly.ptr + (long long)bE * ly.sb;
+          for (int j = 0; j < ncols; ++j) {
+            e_mbar_wait(empty0 + slot * 8, ph ^ 1u);
+            const int ix = xa - 1 + j;
+            const bool cin = (ix >= 0) && (ix < ly.W);
+            const uint32_t fb = full0 + slot * 8;
+            e_mbar_expect_tx(fb, kSlotBytes);
+#pragma unroll
+            for (int ki = 0; ki < K; ++ki) {
+              const int iy = y - 1 + ki;
+              const bool ok = cin && iy >= 0 && iy < ly.H;
+              e_bulk_g2s(e_smem_u32(ring + ((size_t)slot * K + ki) * NCH),
+                         ok ? src + (long long)iy * ly.sh + (long long)ix * ly.sw : fp.zero_row, kRowBytes, fb);
+            }
+            if (++slot == kRingL) { slot = 0; ph ^= 1u; }
+          }
+        }
+      }
+    } else {
+      // ================================================================ consumers (FT)
+      const bool hasA = (bA >= 0) && p.layernorm, hasB = (bE >= 0);
+      constexpr int NW = FT / 32;
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+      // one statistics slot: K tokens of image bA (all channels of this thread's share), sum and sum of squares
+      auto stats_slot = [&]() {
+        e_mbar_wait_spin(full0 + slot * 8, ph);
+        const uint32_t base = ring_a + slot * kSlotBytes;
+#pragma unroll
+        for (int ki = 0; ki < K; ++ki)
+#pragma unroll
+          for (int c = 0; c < TCH; c += 2) {
+            const float2 v = e_lds64(base + (uint32_t)(ki * NCH + c) * 4u);
+            s2 = __fadd2_rn(s2, v);
+            q2 = __ffma2_rn(v, v, q2);
+          }
+        __syncwarp();
+        if (lane == 0) e_mbar_arrive(empty0 + slot * 8);
+        if (++slot == kRingL) { slot = 0; ph ^= 1u; }
+      };
+      // per-warp partial of layer l -> global (no CTA barrier); fp64 from here on
+      auto stats_flush = [&](int l) {
+        const float s = warp_sum(s2.x + s2.y), qq = warp_sum(q2.x + q2.y);
+        if (lane == 0) {
+          double* o = fp.stats + ((((long long)bA * p.L + l) * fp.S + sg) * NW + warp) * 2;
+          o[0] = (double)s;
+          o[1] = (double)qq;
+        }
+        s2 = make_float2(0.f, 0.f);
+        q2 = make_float2(0.f, 0.f);
+      };
+      // ---- phase A: this item's share of the LayerNorm statistics of image bA, published per warp (no CTA barrier)
+      if (hasA) {
+        for (int l = 0; l < p.L; ++l) {
+          for (int t = 0; t < nA; ++t) stats_slot();
+          stats_flush(l);
+        }
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(fp.done + bA, 1);
+        }
+      }
+      // ---- phase B: embed slice sg of image bE
+      if (hasB) {
+        if (p.layernorm) {
+          if (tid == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(fp.done + bE) < fp.S * NW) {
+              __nanosleep(100);
+              if (clock64() - t0 > 4000000000LL) __trap();     // a broken schedule must fail the launch, never hang the GPU
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(FT) : "memory");
+          if (warp == 0) {
+            for (int l = 0; l < p.L; ++l) {
+              const double* st = fp.stats + (((long long)bE * p.L + l) * fp.S) * NW * 2;
+              double a = 0, c2 = 0;
+              for (int i = lane; i < fp.S * NW; i += 32) { a += __ldcg(st + 2 * i); c2 += __ldcg(st + 2 * i + 1); }
+              a = warp_sum(a);
+              c2 = warp_sum(c2);
+              const double n = (double)p.layers[l].C * p.layers[l].H * p.layers[l].W;
+              const double m = a / n;
+              double var = c2 / n - m * m;
+              if (var < 0) var = 0;
+              if (lane == 0) { s_mu[l] = (float)m; s_rs[l] = (float)(1.0 / sqrt(var + (double)p.eps)); }
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(FT) : "memory");
+        }
+        const long long row0 = ((long long)bE * p.h0 + y) * p.w0;
+        const bool yedge = (y == 0) || (y == p.h0 - 1);
+        for (int l = 0; l < p.L; ++l) {
+          const LayerDev& ly = p.layers[l];
+          const float mu = p.layernorm ? s_mu[l] : 0.f, rs = p.layernorm ? s_rs[l] : 1.f;
+          const float nmr = -mu * rs;
+          const float2 nmr2 = make_float2(nmr, nmr);
+          // outputs of period tid at [tid * NOUT, + NOUT), of period tid + FT at FT * NOUT further
+          long long idx = (row0 + xa) * p.ldz + (long long)l * fp.t_stride + (long long)tid * NOUT;
+          float2 v[CPP][K][K];   // [channel][ki][physical column slot]; .x = first period, .y = second
+          float* na = s_nacc + tid;
+          auto step = [&](auto rot_tag, int j) {
+            constexpr int ROT = decltype(rot_tag)::value;
+            constexpr int SLOT = (ROT + K - 1) % K;
+            e_mbar_wait_spin(full0 + slot * 8, ph);
+            const uint32_t base = ring_t + slot * kSlotBytes;
+            e_load_row3<0, NCH, FT * CPP>(base, v[0][0][SLOT], v[1][0][SLOT], v[2][0][SLOT]);
+            e_load_row3<1, NCH, FT * CPP>(base, v[0][1][SLOT], v[1][1][SLOT], v[2][1][SLOT]);
+            e_load_row3<2, NCH, FT * CPP>(base, v[0][2][SLOT], v[1][2][SLOT], v[2][2][SLOT]);
+            __syncwarp();
+            if (lane == 0) e_mbar_arrive(empty0 + slot * 8);
+            if (++slot == kRingL) { slot = 0; ph ^= 1u; }
+            if (j < K - 1) return;                         // the window is not full yet
+            float2 out[NOUT];
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) {
+              float2 acc_o = nmr2;
+#pragma unroll
+              for (int jj = 0; jj < R; ++jj) {
+                const int r = o * R + jj;
+                const int f0 = (r * A) / B, f1 = ((r + 1) * A + B - 1) / B;
+                float2 sacc = v[f0 / (K * K)][(f0 % (K * K)) / K][((f0 % K) + ROT) % K];
+#pragma unroll
+                for (int f = 0; f < A; ++f)
+                  if (f > f0 && f < f1) sacc = __fadd2_rn(sacc, v[f / (K * K)][(f % (K * K)) / K][((f % K) + ROT) % K]);
+                const float cf = rs * (1.0f / (float)(R * (f1 - f0)));
+                acc_o = __ffma2_rn(sacc, make_float2(cf, cf), acc_o);
+              }
+              out[o] = acc_o;
+            }
+            const int x = xa + j - (K - 1);
+            if (yedge || x == 0 || x == p.w0 - 1) {          // warp-uniform, a few percent of the positions
+              // taps outside the map were staged as zeros; the reference pads after the LayerNorm, i.e. they must count as
+              // mu before the affine: add mu * rstd * (missing taps of the window) / (window size)
+              float bad[K][K];
+#pragma unroll
+              for (int ki = 0; ki < K; ++ki)
+#pragma unroll
+                for (int kj = 0; kj < K; ++kj) {
+                  const int iy = y - 1 + ki, ix = x - 1 + kj;
+                  bad[ki][kj] = (iy >= 0 && iy < ly.H && ix >= 0 && ix < ly.W) ? 0.f : 1.f;
+                }
+#pragma unroll
+              for (int o = 0; o < NOUT; ++o) {
+                float corr = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < R; ++jj) {
+                  const int r = o * R + jj;
+                  const int f0 = (r * A) / B, f1 = ((r + 1) * A + B - 1) / B;
+                  float cnt = 0.f;
+#pragma unroll
+                  for (int f = 0; f < A; ++f)
+                    if (f >= f0 && f < f1) cnt += bad[(f % (K * K)) / K][f % K];
+                  corr = fmaf(cnt, 1.0f / (float)(R * (f1 - f0)), corr);
+                }
+                const float add = -nmr * corr;
+                out[o] = __fadd2_rn(out[o], make_float2(add, add));
+              }
+            }
+            if constexpr (WZ) {
+#pragma unroll
+              for (int o = 0; o + 4 <= NOUT; o += 4) {
+                *reinterpret_cast<float4*>(p.Z + idx + o) = make_float4(out[o].x, out[o + 1].x, out[o + 2].x, out[o + 3].x);
+                *reinterpret_cast<float4*>(p.Z + idx + FT * NOUT + o) = make_float4(out[o].y, out[o + 1].y, out[o + 2].y, out[o + 3].y);
+              }
+            }
+            // fp16 operand rows (16-byte stores) and the squared norm of the ROUNDED values
+            float2 nv2 = make_float2(0.f, 0.f);
+            __half* ph_ = reinterpret_cast<__half*>(p.Zhi) + idx;
+#pragma unroll
+            for (int half_ = 0; half_ < 2; ++half_) {
+#pragma unroll
+              for (int o = 0; o + 8 <= NOUT; o += 8) {
+                __align__(16) __half2 h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  h[i] = half_ == 0 ? __floats2half2_rn(out[o + 2 * i].x, out[o + 2 * i + 1].x)
+                                    : __floats2half2_rn(out[o + 2 * i].y, out[o + 2 * i + 1].y);
+                  const float2 f = __half22float2(h[i]);
+                  nv2 = __ffma2_rn(f, f, nv2);
+                }
+                *reinterpret_cast<uint4*>(ph_ + half_ * (FT * NOUT) + o) = *reinterpret_cast<const uint4*>(h);
+              }
+              if constexpr (NOUT == 4) {
+                __align__(8) __half2 h[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  h[i] = half_ == 0 ? __floats2half2_rn(out[2 * i].x, out[2 * i + 1].x) : __floats2half2_rn(out[2 * i].y, out[2 * i + 1].y);
+                  const float2 f = __half22float2(h[i]);
+                  nv2 = __ffma2_rn(f, f, nv2);
+                }
+                *reinterpret_cast<uint2*>(ph_ + half_ * (FT * NOUT)) = *reinterpret_cast<const uint2*>(h);
+              }
+            }
+            const float nv = nv2.x + nv2.y;
+            *na = (l == 0) ? nv : (*na + nv);
+            na += FT;
+            idx += p.ldz;
+          };
+          for (int j0 = 0; j0 < ncols; j0 += 3) {
+            step(std::integral_constant<int, 1>{}, j0);
+            if (j0 + 1 < ncols) step(std::integral_constant<int, 2>{}, j0 + 1);
+            if (j0 + 2 < ncols) step(std::integral_constant<int, 0>{}, j0 + 2);
+          }
+        }
+        // squared norms of the operand rows of this segment: fixed summation order (bit-reproducible)
+        asm volatile("bar.sync 1, %0;" ::"n"(FT) : "memory");
+        for (int pos = warp; pos < npos; pos += FT / 32) {
+          float a = 0.f;
+#pragma unroll
+          for (int k2 = 0; k2 < FT / 32; ++k2) a += s_nacc[pos * FT + lane + 32 * k2];
+          a = warp_sum(a);
+          if (lane == 0) fp.n2[row0 + xa + pos] = a;
+        }
+      }
+    }
+    if (!producer) asm volatile("bar.sync 1, %0;" ::"n"(FT) : "memory");      // s_nacc / s_mu are reused by the next item
   }
 }
 
@@ -1572,11 +1930,16 @@ static bool fused_eligible(const Plan& plan, const EmbedParams& p, const Periodi
   return true;
 }
 
+static constexpr size_t kZeroRowBytes = 4096;   // lean kernel: a row of zeros stands in for taps outside the map (<= 768 channels)
+
 static size_t fused_ws_bytes(int L, int B, int h0, int w0) {
   const int nxseg = ceil_div(w0, kMaxSeg);
   const size_t S = (size_t)h0 * nxseg;
-  return (((size_t)B * L * S * 2 * sizeof(double) + 255) & ~(size_t)255) + ((((size_t)B + 64) * sizeof(int) + 255) & ~(size_t)255);
+  return (((size_t)B * L * S * 4 * 2 * sizeof(double) + 255) & ~(size_t)255) + ((((size_t)B + 64) * sizeof(int) + 255) & ~(size_t)255) +
+         kZeroRowBytes;    // statistics: one partial per slice (general kernel) or per slice and consumer warp (lean kernel, <= 4)
 }
+
+static int g_fused_lean = 1;      // debug knob (ac_debug_set key 9): 0 = always the general fused kernel
 
 static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, int num_sms, cudaStream_t st) {
   FusedParams fp;
@@ -1593,13 +1956,39 @@ static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, 
   fp.gx = ceil_div(pr.nperiods, kFT * kPP);
   fp.t_stride = pr.ncols;
   fp.n_items = (long long)(p.B + fp.LA) * fp.S;
-  const size_t stats_b = ((size_t)p.B * p.L * fp.S * 2 * sizeof(double) + 255) & ~(size_t)255;
+  const size_t stats_b = ((size_t)p.B * p.L * fp.S * 4 * 2 * sizeof(double) + 255) & ~(size_t)255;
   fp.stats = (double*)ws;
   fp.done = (int*)((char*)ws + stats_b);
   fp.counter = (unsigned int*)(fp.done + p.B);
-  const long long words = (long long)p.B + 1;
+  // done[B], the claim counter and (after the 256-byte aligned counters) the zero row are cleared in one launch
+  const size_t ctr_b = (((size_t)p.B + 64) * sizeof(int) + 255) & ~(size_t)255;
+  fp.zero_row = (const float*)((char*)fp.done + ctr_b);
+  const long long words = (long long)((ctr_b + kZeroRowBytes) / 4);
   zero_words_kernel<<<(unsigned)std::min<long long>((words + 255) / 256, 64), 256, 0, st>>>((unsigned int*)fp.done, words);
   AC_LAUNCH_CHECK();
+  // lean kernel: fp16 operands + norms (+ fp32 Z), every consumer thread owns two periods of every layer
+  const bool lean_out = g_fused_lean && p.Zhi && !p.Zlo && p.op_dtype == AC_DT_F16 && n2 && pr.R == 1 && pr.A == 27 &&
+                        (p.ldz % 8 == 0) && (pr.ncols % 8 == 0) && (reinterpret_cast<uintptr_t>(p.Zhi) % 16 == 0) &&
+                        (!p.Z || reinterpret_cast<uintptr_t>(p.Z) % 16 == 0);
+#define XL(b, ft)                                                                                                     \
+  if (lean_out && pr.B == b && pr.nperiods == ft * kPP && p.layers[0].C == ft * kPP * 3) {                            \
+    const size_t smem = ((size_t)kRingL * 3 * ft * kPP * 3 + (size_t)kMaxSeg * ft) * sizeof(float);                   \
+    const int cps = (ft == 128) ? std::min(g_fused_cps, 3) : 5;                                                             \
+    const int grid_l = (int)std::min<long long>(fp.n_items, (long long)num_sms * cps);                                \
+    if (p.Z) {                                                                                                        \
+      auto kern = embed_fused_fast_kernel<27, b, 1, ft, true>;                                                        \
+      AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+      kern<<<grid_l, ft + 32, smem, st>>>(fp);                                                                        \
+    } else {                                                                                                          \
+      auto kern = embed_fused_fast_kernel<27, b, 1, ft, false>;                                                       \
+      AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+      kern<<<grid_l, ft + 32, smem, st>>>(fp);                                                                        \
+    }                                                                                                                 \
+    AC_LAUNCH_CHECK();                                                                                                \
+    return AC_OK;                                                                                                     \
+  }
+  XL(8, 128) XL(4, 128) XL(16, 64)
+#undef XL
   const int grid = (int)std::min<long long>(fp.n_items, (long long)num_sms * g_fused_cps);
 #define X(a, b, r)                                                                                                   \
   if (pr.A == a && pr.B == b && pr.R == r) {                                                                         \
@@ -1859,6 +2248,7 @@ extern "C" int ac_debug_set_embed(int value) {
   return AC_OK;
 }
 extern "C" int ac_debug_set_fused(int key, int value) {
+  if (key == 9 && (value == 0 || value == 1)) { g_fused_lean = value; return AC_OK; }
   if (key == 7 && value >= 1 && value <= 64) { g_fused_la = value; return AC_OK; }
   if (key == 8 && value >= 1 && value <= 3) { g_fused_cps = value; return AC_OK; }
   return AC_ERR_INVALID;

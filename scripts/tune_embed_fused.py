@@ -38,7 +38,15 @@ for want_z in (False, True):
     ms = timed(want_z)
     print("want_z=%s  per-layer launches (+ statistics pass + row norms): %.3f ms  = %.0f GB/s algorithmic (%.1f MB)" % (want_z, ms, nbytes / ms / 1e6, nbytes / 1e6))
     lib.ac_debug_set(2, 0)
-    for cps in (3, 2):
+    lib.ac_debug_set(9, 1)
+    for la in (1, 2, 4):
+        lib.ac_debug_set(7, la)
+        ms = timed(want_z)
+        print("want_z=%s  lean fused  look-ahead %d images: %.3f ms  = %.0f GB/s algorithmic = %.3f of 6547.8" % (
+            want_z, la, ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / 6547.8), flush=True)
+    lib.ac_debug_set(7, 2)
+    lib.ac_debug_set(9, 0)
+    for cps in (3,):
         for la in (1, 2, 3, 4, 8):
             lib.ac_debug_set(7, la)
             lib.ac_debug_set(8, cps)
@@ -47,3 +55,4 @@ for want_z in (False, True):
                 want_z, cps, la, ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / 6547.8), flush=True)
 lib.ac_debug_set(7, 2)
 lib.ac_debug_set(8, 3)
+lib.ac_debug_set(9, 1)
