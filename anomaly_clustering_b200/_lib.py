@@ -50,6 +50,7 @@ SIGNATURES = {
     "ac_strerror": (c_char_p, [c_int]),
     "ac_device_ok": (c_int, [c_int]),
     "ac_last_cuda_error": (c_int, []),
+    "ac_last_watchdog": (c_int, []),
     "ac_embed_workspace_bytes": (c_size_t, [POINTER(AcLayer), c_int, c_int, c_int, c_int, c_int, c_int]),
     "ac_embed": (
         c_int,
@@ -148,4 +149,7 @@ def check(code: int, what: str = "") -> None:
     msg = lib.ac_strerror(code).decode()
     if code == AC_ERR_CUDA:
         msg += " [cudaError %d]" % lib.ac_last_cuda_error()
+        wd = lib.ac_last_watchdog()
+        if wd:
+            msg += " [pipeline watchdog fired in wait %d of the tensor-core kernel, see ac_last_watchdog in include/ac_b200.h]" % wd
     raise AcError(code, "%s: %s (%d)" % (what or "libac_b200", msg, code))

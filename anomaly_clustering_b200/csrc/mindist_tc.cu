@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 namespace ac {
@@ -131,7 +132,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > kWatchdogCycles) {  // pipeline deadlock: report and kill the launch, never hang the GPU
-      if (err) atomicExch(err, code);
+      if (err) *reinterpret_cast<volatile int*>(err) = code;   // host-mapped flag: still readable after the trap (ac_last_watchdog)
       __threadfence_system();
       __trap();
     }
@@ -153,7 +154,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (clock64() - t0 > kWatchdogCycles) {
-      if (err) atomicExch(err, code);
+      if (err) *reinterpret_cast<volatile int*>(err) = code;
       __threadfence_system();
       __trap();
     }
@@ -782,6 +783,24 @@ static uint32_t make_idesc(int M, int N, bool bf16) {
   return d;
 }
 
+// Watchdog flag in pinned, mapped host memory (one per process, every device sees it through UVA): device memory cannot be
+// read back once the kernel has trapped, this can.
+static int* g_wd_host = nullptr;
+static int* g_wd_dev = nullptr;
+static std::once_flag g_wd_once;
+static int* watchdog_flag() {
+  std::call_once(g_wd_once, [] {
+    int* h = nullptr;
+    if (cudaHostAlloc((void**)&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    *h = 0;
+    int* d = nullptr;
+    if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) { (void)cudaGetLastError(); d = h; }
+    g_wd_host = h;
+    g_wd_dev = d;
+  });
+  return g_wd_dev;   // null when the allocation failed: the kernels then only trap
+}
+
 static int g_tc_cta_group = 2;   // test hook (ac_debug_set): 1 = single-CTA MMAs, 2 = CTA pairs
 static int g_tc_dynamic = 1;  // knob 4: dynamic unit scheduler (work stealing); measured 7 % faster than static round-robin
 static int g_tc_l2hint = 0;  // debug knob 3: L2 evict_last policy on operand loads (measured: no gain, off)
@@ -831,7 +850,7 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   nt = ceil_div(P, wmain);
   const int wlast = ceil_div(P - (nt - 1) * wmain, 16) * 16;
   prm.nt = nt; prm.wmain = wmain; prm.wlast = wlast;
-  prm.qn2 = Qn2; prm.bn2 = Bn2; prm.dmin = dmin; prm.err = err_flag;
+  prm.qn2 = Qn2; prm.bn2 = Bn2; prm.dmin = dmin; prm.err = watchdog_flag();
   prm.Mq = Mq; prm.nb_img = nb_img; prm.P = P; prm.D = D;
   prm.nkb = ceil_div(D, kBlockK);
   prm.nseg = x3 ? 3 : 1;
@@ -892,6 +911,13 @@ int launch_mindist_simt(const float* Q, long long Mq, const float* Bk, int nb_im
 
 using namespace ac;
 
+extern "C" int ac_last_watchdog(void) {
+  if (!g_wd_host) return 0;
+  const int code = *reinterpret_cast<volatile int*>(g_wd_host);
+  *reinterpret_cast<volatile int*>(g_wd_host) = 0;
+  return code;
+}
+
 // test / tuning hook (not part of the public header): key 0 = cta group (1|2), key 1 = M-blocks per raster group
 extern "C" int ac_debug_set_embed(int value);
 extern "C" int ac_debug_set_refine(int mb);
@@ -909,21 +935,47 @@ extern "C" int ac_debug_set(int key, int value) {
   return AC_ERR_INVALID;
 }
 
-__global__ void reduce_weights_sym_kernel(const float* __restrict__ rowmin, const float* __restrict__ colmin, long long Mq, int nb_img,
-                                          int Pq, int q_img0, const int* __restrict__ groups, float* __restrict__ w) {
-  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (r >= Mq) return;
-  const int i = q_img0 + (int)(r / Pq);
+// w[r] = mean over the other images j of the category of sqrt(d2(r, j)), d2 taken from whichever of the two minima the
+// ownership rule says was written.  A block handles 64 query rows x 4 quarters of the bank-image range (a sharded run has
+// only ~10^4 rows per rank: one thread per row left most SMs idle and ran ~100 dependent loads per thread); the four
+// partial sums are added in a fixed order, so the result does not depend on the launch geometry.
+__global__ void __launch_bounds__(256) reduce_weights_sym_kernel(const float* __restrict__ rowmin, const float* __restrict__ colmin,
+                                                                 long long Mq, int nb_img, int Pq, int q_img0,
+                                                                 const int* __restrict__ groups, float* __restrict__ w) {
+  __shared__ float s_part[4][64];
+  const int rr = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const long long r = blockIdx.x * 64LL + rr;
   float s = 0.f;
-  int cnt = 0;
-  const int j0 = groups ? groups[2 * i] : 0, j1 = groups ? j0 + groups[2 * i + 1] : nb_img;   // the image's own category
-  for (int j = j0; j < j1; ++j) {
-    if (j == i) continue;
-    const float d2 = pair_owned_grouped(groups, i, j, nb_img) ? __ldg(rowmin + (long long)j * Mq + r) : __ldg(colmin + (long long)j * Mq + r);
-    s += sqrtf(d2);   // same left-to-right order as the reference's torch.mean over the cat'ed columns
-    ++cnt;
+  int j0 = 0, j1 = 0, i = 0;
+  if (r < Mq) {
+    i = q_img0 + (int)(r / Pq);
+    j0 = groups ? groups[2 * i] : 0;                       // the image's own category
+    j1 = groups ? j0 + groups[2 * i + 1] : nb_img;
+    const int len = j1 - j0, chunk = (len + 3) >> 2;
+    const int ja = j0 + part * chunk, jb = min(j1, ja + chunk);
+    for (int jq = ja; jq < jb; jq += 8) {
+      float d[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = jq + u;
+        d[u] = -1.f;
+        if (j < jb && j != i) {
+          const float* src = pair_owned_grouped(groups, i, j, nb_img) ? rowmin : colmin;
+          d[u] = __ldg(src + (long long)j * Mq + r);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (d[u] >= 0.f) s += sqrtf(d[u]);
+    }
   }
-  w[r] = cnt > 0 ? s / (float)cnt : nanf("");
+  s_part[part][rr] = s;
+  __syncthreads();
+  if (part == 0 && r < Mq) {
+    const int cnt = (j1 - j0) - ((i >= j0 && i < j1) ? 1 : 0);
+    const float tot = ((s_part[0][rr] + s_part[1][rr]) + s_part[2][rr]) + s_part[3][rr];
+    w[r] = cnt > 0 ? tot / (float)cnt : nanf("");
+  }
 }
 
 static int min_dist_sym_impl(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
@@ -988,7 +1040,7 @@ extern "C" int ac_reduce_weights_sym_ex(const float* rowmin_d2, const float* col
   int rc = check_device();
   if (rc) return rc;
   if (Mq == 0) return AC_OK;
-  reduce_weights_sym_kernel<<<(unsigned)((Mq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowmin_d2, colmin_d2, Mq, nb_img, Pq, q_img0,
+  reduce_weights_sym_kernel<<<(unsigned)((Mq + 63) / 64), 256, 0, (cudaStream_t)stream>>>(rowmin_d2, colmin_d2, Mq, nb_img, Pq, q_img0,
                                                                                             groups, w);
   AC_LAUNCH_CHECK();
   return AC_OK;

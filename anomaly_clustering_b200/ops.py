@@ -20,6 +20,12 @@ def launches() -> int:
     return int(_lib.load().ac_debug_launches())
 
 
+def watchdog_code() -> int:
+    """Which mbarrier wait of the tensor-core kernel timed out (0 = none); readable after the launch has trapped, i.e. after
+    torch reports the sticky CUDA error at the next synchronisation (ac_last_watchdog)."""
+    return int(_lib.load().ac_last_watchdog())
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -68,6 +68,12 @@ const char* ac_strerror(int code);
 int ac_device_ok(int dev);
 /* cudaError_t of the last failing CUDA call made by this library on this thread (0 if none). */
 int ac_last_cuda_error(void);
+/* Pipeline watchdog of the tensor-core kernels (ac_min_dist*): a role that waits > ~10 s on an mbarrier records which
+ * wait it was in host-mapped memory and traps, so the launch fails instead of hanging the GPU; the sticky CUDA error
+ * surfaces at the caller's next synchronisation.  Returns that code (0 = never fired; 1 producer waits for a free stage,
+ * 2 MMA issuer waits for a TMEM buffer, 3 MMA issuer waits for operands, 4 epilogue waits for an accumulator,
+ * 5 / 6 unit queue) and clears it.  Readable after the trap because the flag lives in pinned host memory. */
+int ac_last_watchdog(void);
 
 /* ---- stage 1: feature maps -> patch embeddings Z ----------------------------------------------
  * Replaces AnomalyClusteringCore._embed after the backbone (models/patchcore/patchcore.py:368-431):

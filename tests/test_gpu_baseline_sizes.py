@@ -5,6 +5,9 @@
     config 2  ViT-B/8 shape, 100 images x 784 patches x 4096-d, unsupervised                     (full, ~40 s of oracle)
     config 3  config-2 queries against a 200-image normal bank, supervised + average             (full GPU run; the
               oracle evaluates a subsample of the query images against the FULL bank -- rows are independent)
+    config 4  1,210 images in 10 MVTec-object-sized categories: per-category banks in one batched launch (one category
+              in full + sampled rows of another against the oracle) and the joint 1,210-image bank (sampled image pairs
+              against the oracle's cdist + a float64 reduction of every row)
     config 5  ViT-S/8 at 448x448 shape (3136 patches), tau sweep incl. tau = 0.1                  (5 images)
     stress    config-2 shape with real-data patch norms (45-50) and precision="auto"
 
@@ -238,3 +241,96 @@ def test_config5_geometry_tau_sweep_vs_oracle():
     for ti in range(len(taus)):
         check_tau(res, ti, want[ti])
     assert (res.alpha64.sum(dim=2) - 1).abs().max().item() <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ config 4
+MVTEC_OBJECT_SIZES = [83, 150, 132, 110, 115, 167, 160, 42, 100, 151]
+
+
+@pytest.fixture(scope="module")
+def config4():
+    """The 1,210 config-4 images (10 MVTec-object-sized categories back to back, bench.py's ids) on the device."""
+    ids = [1000 * c + i for c, n in enumerate(MVTEC_OBJECT_SIZES) for i in range(n)]
+    feats, _ = synth.planted_features_device(ids, VITB, device="cuda")
+    return feats
+
+
+def test_config4_per_category_full_size_vs_oracle(config4):
+    """BASELINE config 4 with the reference's semantics (one make_category_data per category, examples/main.py:353): all 10
+    categories, 1,210 images, in ONE batched launch sequence (category table).  The oracle runs the smallest category
+    (42 images) on its own, in full: every w / alpha / X row and the category's distance matrix; a second category is
+    checked through three of its images against that category's full bank."""
+    feats = config4
+    sizes = MVTEC_OBJECT_SIZES
+    res = pipeline.run_categories(feats, sizes, 3, 1, 2048, 4096, [1.0], precision="auto", keep_z=False)
+    assert len(res) == len(sizes) and all(r.w.shape == (n, 784) for r, n in zip(res, sizes))
+    starts = np.cumsum([0] + sizes)
+    c = 7
+    sl = slice(int(starts[c]), int(starts[c + 1]))
+    Z = oracle_embed([f[sl].cpu() for f in feats], 2048, 4096)
+    w = restated.weight_distance_unsupervised(Z)
+    assert ((res[c].w.cpu() - w).abs() / w).max().item() <= 2e-4
+    check_tau(res[c], 0, oracle_stage3(w, Z, [1.0])[0])
+    c = 0
+    sl = slice(int(starts[c]), int(starts[c + 1]))
+    Zc = oracle_embed([f[sl].cpu() for f in feats], 2048, 4096)
+    sample = [0, 40, 82]
+    dm = restated.per_image_min_dist(Zc[sample], Zc)                      # [3, 784, 83]
+    for k, i in enumerate(sample):
+        keep = torch.ones(sizes[c], dtype=torch.bool)
+        keep[i] = False
+        wi = dm[k][:, keep].mean(dim=1)
+        assert ((res[c].w[i].cpu() - wi).abs() / wi).max().item() <= 2e-4
+        a = restated.alpha_from_weights(wi[None], 1.0, stable=True)
+        assert (res[c].alpha64[0][i].cpu() - a[0]).abs().max().item() <= 1e-3
+        assert rel_l2(res[c].X[0][i].cpu().numpy(), restated.weighted_embedding(a, Zc[i:i + 1])[0]) <= 1e-3
+
+
+def test_config4_joint_bank_full_size_sampled_pairs_vs_oracle(config4):
+    """BASELINE config 4 as ONE joint bank (every image against the other 1,209; 948,640 patch rows, 7.4 PFLOP of
+    algorithmic distance work) through the C ABI at full size.  The oracle cannot run 1.46 M image pairs, but the path
+    factorises: (i) the per-pair minima d(r, j) = min_c |z_r - z_(j,c)| (utils.py:226) are checked against the oracle's
+    cdist for sampled image pairs spread over the whole raster -- both orientations of a pair, i.e. the row-min and the
+    column-min side of the symmetric kernel -- and (ii) w = mean over the 1,209 other images is checked for EVERY row
+    against a float64 reduction of those minima."""
+    from anomaly_clustering_b200 import ops
+
+    feats = config4
+    n, P, D = sum(MVTEC_OBJECT_SIZES), 784, 4096
+    q = pipeline.embed_images(feats, 3, 1, 2048, D, "f16", want_z=False)
+    rowmin, colmin = ops.min_dist_sym(q.hi, None, q.n2, 0, q.hi, None, q.n2, n, P, "f16")
+    w = ops.reduce_weights_sym(rowmin, colmin, P, 0).reshape(n, P)
+    torch.cuda.synchronize()
+    assert torch.isfinite(w).all()
+    gen = torch.Generator().manual_seed(4)
+    pairs = [(0, 1), (0, 605), (1209, 0), (604, 1209), (83, 82), (700, 95)] + [tuple(int(v) for v in torch.randint(0, n, (2,), generator=gen)) for _ in range(10)]
+    pairs = [(i, j) for i, j in pairs if i != j]
+    imgs = sorted({i for pr in pairs for i in pr})
+    Zs = oracle_embed([f[imgs].cpu() for f in feats], 2048, D, chunk=8)
+    pos = {g: k for k, g in enumerate(imgs)}
+    from anomaly_clustering_b200.distributed import pair_owned
+
+    def d_gpu(i, j):          # query image i, bank image j
+        d2 = rowmin[j, i * P:(i + 1) * P] if pair_owned(i, j, n) else colmin[i, j * P:(j + 1) * P]
+        return d2.sqrt().cpu()
+
+    for i, j in pairs:
+        for a, b in ((i, j), (j, i)):
+            want = torch.cdist(Zs[pos[a]], Zs[pos[b]]).min(dim=1)[0]
+            got = d_gpu(a, b)
+            assert ((got - want).abs() / want).max().item() <= 3e-4, (a, b)
+    # (ii) the mean over the other images, every row, in float64 on the device
+    ii, jj = torch.arange(n, device="cuda")[:, None], torch.arange(n, device="cuda")[None, :]
+    dd = (jj - ii) % n
+    own = (dd != 0) & ((2 * dd < n) | ((2 * dd == n) & (ii < jj)))                                     # [i, j], the kernel's rule
+    assert all(bool(own[i, j]) == pair_owned(i, j, n) for i, j in pairs)
+    rm = rowmin.reshape(n, n, P).permute(1, 0, 2)            # [i, j, P]: rowmin[j, i*P + p]
+    cm = colmin.reshape(n, n, P)                             # [i, j, P]
+    acc = torch.zeros(n, P, dtype=torch.float64, device="cuda")
+    for j0 in range(0, n, 64):                               # chunks of bank images keep the temporaries small
+        j1 = min(n, j0 + 64)
+        d2 = torch.where(own[:, j0:j1, None], rm[:, j0:j1], cm[:, j0:j1]).double().sqrt()
+        eye = (torch.arange(n, device="cuda")[:, None] == torch.arange(j0, j1, device="cuda")[None, :])
+        acc += torch.where(eye[:, :, None], torch.zeros((), dtype=torch.float64, device="cuda"), d2).sum(dim=1)
+    w64 = acc / (n - 1)
+    assert ((w.double() - w64).abs() / w64).max().item() <= 2e-6
