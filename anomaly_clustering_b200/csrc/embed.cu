@@ -736,6 +736,10 @@ struct FusedParams {
   int S, LA, nperiods, gx, t_stride;
   long long n_items;       // (B + LA) * S
   const float* zero_row;   // >= 4 KB of zeros (lean kernel: stands in for taps outside the map)
+  unsigned long long* murs;  // [B][L] (mean, 1/std) packed as two floats, all-ones until the last statistics warp of the image wrote it (lean kernel)
+  int pd;                  // lean kernel: items the L2 prefetch of the statistics rows runs ahead of the claims (0 = off)
+  int cs;                  // lean kernel: operand rows stored with the streaming (evict-first) policy
+  int l2pol;               // lean kernel: L2 policy of the map loads: 0 normal, 1 evict_last, 2 evict_last except the last use of a row
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -1127,6 +1131,47 @@ __device__ __forceinline__ void e_load_row3(uint32_t base, float2& a, float2& b,
   c = make_float2(e_lds32<(KI * NCH_ + 2) * 4>(base), e_lds32<(KI * NCH_ + HALF + 2) * 4>(base));
 }
 
+// "The data is the flag": a partial statistic (sum, sum of squares) and a final (mean, 1/std) travel as ONE 64-bit relaxed
+// store into a slot that holds all-ones until then (no arithmetic produces that pattern: NaNs come out canonical,
+// 0x7fffffff), and readers poll the slot itself.  No release / acquire fences: a gpu-scope release made every consumer
+// warp wait for all its outstanding operand stores (MEMBAR + ERRBAR: 6 % of the samples in the round-2 capture), an
+// acquire invalidates L1 on every poll.
+static constexpr unsigned long long kUnset = ~0ull;
+__device__ __forceinline__ int e_atom_add_relaxed(int* p, int v) {
+  int old;
+  asm volatile("atom.add.relaxed.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void e_st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long e_ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long e_pack2(float a, float b) {
+  return (unsigned long long)__float_as_uint(a) | ((unsigned long long)__float_as_uint(b) << 32);
+}
+// polls a slot until it is set; a broken schedule must fail the launch, never hang the GPU
+__device__ __forceinline__ unsigned long long e_wait_set(const unsigned long long* p, unsigned long long v) {
+  if (v != kUnset) return v;
+  const long long t0 = clock64();
+  while ((v = e_ld_relaxed_u64(p)) == kUnset) {
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+  return v;
+}
+__device__ __forceinline__ void e_bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void e_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 static constexpr int kRingL = 7;         // ring depth of the lean kernel (72 KB of shared memory per CTA at 768 channels, 3 CTAs per SM)
 static constexpr int kItemQ = 2;         // items the producer may be ahead of the consumers
 
@@ -1147,7 +1192,6 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
   __shared__ __align__(8) uint64_t s_full[kRingL], s_empty[kRingL];
   __shared__ __align__(8) uint64_t s_qfull[kItemQ], s_qempty[kItemQ];
   __shared__ long long s_items[kItemQ];
-  __shared__ float s_mu[kMaxLayers], s_rs[kMaxLayers];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = (warp == FT / 32);
   if (tid == 0) {
@@ -1176,6 +1220,19 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
   // statistics of its image cannot deadlock.
   uint32_t qs = 0, qph = 0;
   if (producer && lane != 0) return;
+  // L2 policies of the map loads: the maps must survive in L2 from their statistics read to their last embed read while
+  // 1.3x their volume of operand rows streams out through the same cache
+  uint64_t pol_keep = 0, pol_last = 0;
+  if (producer) {
+    if (fp.l2pol == 0) {
+      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+      pol_last = pol_keep;
+    } else {
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+      pol_last = pol_keep;
+      if (fp.l2pol == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_last));
+    }
+  }
   for (;;) {
     long long item;
     if (producer) {
@@ -1207,42 +1264,62 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
       // statistics slots of image bA first (they never wait for anything), then the embed slots of image bE.  (Spreading the
       // statistics slots through the embed loop hides their DRAM latency but delays done[bA] to the end of an item that
       // itself waits for done[bE]: the images then advance LA per item time -- measured 2.5 / 1.3 / 0.65 ms at LA 1 / 2 / 4.)
+      // The producer is ONE thread and every slot costs it a serial chain (ncu, round 2: 188 instructions per slot with the
+      // addresses recomputed per row -- 1 250 cycles per slot and CTA, the consumers waited for data 23 % of their time), so
+      // everything that does not change inside an item is hoisted: per row one running pointer, per slot one add and one
+      // select per row.
       const bool hasA = (bA >= 0) && p.layernorm, hasB = (bE >= 0);
+      const uint32_t ring_u = e_smem_u32(ring);
+      if (fp.pd > 0 && p.layernorm) {
+        // statistics rows of the item claimed fp.pd claims from now: DRAM -> L2 ahead of time, so that the statistics slots
+        // at the head of that item's in-order ring are L2 hits like its embed slots
+        const long long it2 = item + fp.pd;
+        const int q2 = (int)(it2 / fp.S);
+        if (q2 < p.B) {
+          const int sg2 = (int)(it2 - (long long)q2 * fp.S);
+          const int y2 = sg2 / p.nxseg, xs2 = sg2 - y2 * p.nxseg;
+          const int xa2 = xs2 * p.xseg_len, np2 = min(p.w0, xa2 + p.xseg_len) - xa2;
+          for (int l = 0; l < p.L; ++l) {
+            const LayerDev& ly = p.layers[l];
+            if (ly.sw == NCH)      // the tokens of a row are contiguous
+              e_prefetch_l2(ly.ptr + (long long)q2 * ly.sb + (long long)y2 * ly.sh + (long long)xa2 * ly.sw, (uint32_t)np2 * kRowBytes);
+          }
+        }
+      }
       if (hasA) {
         for (int l = 0; l < p.L; ++l) {
           const LayerDev& ly = p.layers[l];
-          const float* srcA = ly.ptr + (long long)bA * ly.sb + (long long)y * ly.sh + (long long)xa * ly.sw;
-          for (int t = 0; t < nA; ++t) {
+          const long long sw = ly.sw;
+          const float* cur = ly.ptr + (long long)bA * ly.sb + (long long)y * ly.sh + (long long)xa * sw;
+          int rem = npos;                                    // tokens left (>= 1 at every slot)
+          for (int t = 0; t < nA; ++t, rem -= K, cur += K * sw) {
             e_mbar_wait(empty0 + slot * 8, ph ^ 1u);
-            const uint32_t fb = full0 + slot * 8;
+            const uint32_t fb = full0 + slot * 8, dst = ring_u + slot * kSlotBytes;
             e_mbar_expect_tx(fb, kSlotBytes);
 #pragma unroll
-            for (int ki = 0; ki < K; ++ki) {
-              const int tok = K * t + ki;
-              e_bulk_g2s(e_smem_u32(ring + ((size_t)slot * K + ki) * NCH), (tok < npos) ? srcA + (long long)tok * ly.sw : fp.zero_row,
-                         kRowBytes, fb);
-            }
+            for (int ki = 0; ki < K; ++ki) e_bulk_g2s_hint(dst + ki * kRowBytes, (ki < rem) ? cur + ki * sw : fp.zero_row, kRowBytes, fb, pol_keep);
             if (++slot == kRingL) { slot = 0; ph ^= 1u; }
           }
         }
       }
       if (hasB) {
+        // column xa - 1 + j lies outside the map only at j == 0 of the first segment and at the last j of the last segment
+        const int jlo = (xa == 0) ? 0 : -1, jhi = (xb == p.w0) ? ncols - 1 : -1;
         for (int l = 0; l < p.L; ++l) {
           const LayerDev& ly = p.layers[l];
-          const float* src = ly.ptr + (long long)bE * ly.sb;
-          for (int j = 0; j < ncols; ++j) {
+          const long long sw = ly.sw;
+          const float* r0 = ly.ptr + (long long)bE * ly.sb + (long long)(xa - 1) * sw + (long long)(y - 1) * ly.sh;
+          const float* r1 = r0 + ly.sh;
+          const float* r2 = r1 + ly.sh;
+          const bool ok0 = (y >= 1), ok2 = (y + 1 < ly.H);
+          for (int j = 0; j < ncols; ++j, r0 += sw, r1 += sw, r2 += sw) {
             e_mbar_wait(empty0 + slot * 8, ph ^ 1u);
-            const int ix = xa - 1 + j;
-            const bool cin = (ix >= 0) && (ix < ly.W);
-            const uint32_t fb = full0 + slot * 8;
+            const bool cin = (j != jlo) && (j != jhi);
+            const uint32_t fb = full0 + slot * 8, dst = ring_u + slot * kSlotBytes;
             e_mbar_expect_tx(fb, kSlotBytes);
-#pragma unroll
-            for (int ki = 0; ki < K; ++ki) {
-              const int iy = y - 1 + ki;
-              const bool ok = cin && iy >= 0 && iy < ly.H;
-              e_bulk_g2s(e_smem_u32(ring + ((size_t)slot * K + ki) * NCH),
-                         ok ? src + (long long)iy * ly.sh + (long long)ix * ly.sw : fp.zero_row, kRowBytes, fb);
-            }
+            e_bulk_g2s_hint(dst, (cin && ok0) ? r0 : fp.zero_row, kRowBytes, fb, pol_last);
+            e_bulk_g2s_hint(dst + kRowBytes, cin ? r1 : fp.zero_row, kRowBytes, fb, pol_keep);
+            e_bulk_g2s_hint(dst + 2 * kRowBytes, (cin && ok2) ? r2 : fp.zero_row, kRowBytes, fb, pol_keep);
             if (++slot == kRingL) { slot = 0; ph ^= 1u; }
           }
         }
@@ -1268,60 +1345,74 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
         if (lane == 0) e_mbar_arrive(empty0 + slot * 8);
         if (++slot == kRingL) { slot = 0; ph ^= 1u; }
       };
-      // per-warp partial of layer l -> global (no CTA barrier); fp64 from here on
+      // per-warp partial of layer l -> its slot in global memory (one 64-bit relaxed store, see kUnset)
+      unsigned long long* part = reinterpret_cast<unsigned long long*>(fp.stats);
       auto stats_flush = [&](int l) {
         const float s = warp_sum(s2.x + s2.y), qq = warp_sum(q2.x + q2.y);
-        if (lane == 0) {
-          double* o = fp.stats + ((((long long)bA * p.L + l) * fp.S + sg) * NW + warp) * 2;
-          o[0] = (double)s;
-          o[1] = (double)qq;
-        }
+        if (lane == 0) e_st_relaxed_u64(part + (((long long)bA * p.L + l) * fp.S + sg) * NW + warp, e_pack2(s, qq));
         s2 = make_float2(0.f, 0.f);
         q2 = make_float2(0.f, 0.f);
       };
-      // ---- phase A: this item's share of the LayerNorm statistics of image bA, published per warp (no CTA barrier)
+      // ---- phase A: this item's share of the LayerNorm statistics of image bA, published per warp (no CTA barrier).
+      // The warp that publishes the LAST partial of an image folds all of them (fixed order, fp64) into mean and 1/std
+      // once; the embed phases of that image then read two floats per layer.  (Every embed item used to re-reduce the
+      // S * NW partials behind two CTA barriers: 11 % of the consumers' samples in the round-2 ncu capture.)
       if (hasA) {
         for (int l = 0; l < p.L; ++l) {
           for (int t = 0; t < nA; ++t) stats_slot();
           stats_flush(l);
         }
-        if (lane == 0) {
-          __threadfence();
-          atomicAdd(fp.done + bA, 1);
+        int old = 0;
+        if (lane == 0) old = e_atom_add_relaxed(fp.done + bA, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == fp.S * NW - 1) {
+          // every partial of the image has been stored (the counter says so) but not necessarily become visible: wait per slot
+          const int n = fp.S * NW;
+          for (int l = 0; l < p.L; ++l) {
+            const unsigned long long* st = part + (((long long)bA * p.L + l) * fp.S) * NW;
+            double a = 0, c2 = 0;
+            for (int i0 = 0; i0 < n; i0 += 32 * 8) {
+              unsigned long long v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 32 + lane;
+                v[u] = (i < n) ? e_ld_relaxed_u64(st + i) : 0ull;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 32 + lane;
+                if (i < n) {
+                  const unsigned long long x = e_wait_set(st + i, v[u]);
+                  a += (double)__uint_as_float((unsigned int)x);
+                  c2 += (double)__uint_as_float((unsigned int)(x >> 32));
+                }
+              }
+            }
+            a = warp_sum(a);
+            c2 = warp_sum(c2);
+            const double nn = (double)p.layers[l].C * p.layers[l].H * p.layers[l].W;
+            const double m = a / nn;
+            double var = c2 / nn - m * m;
+            if (var < 0) var = 0;
+            if (lane == 0) e_st_relaxed_u64(fp.murs + (long long)bA * p.L + l, e_pack2((float)m, (float)(1.0 / sqrt(var + (double)p.eps))));
+          }
         }
       }
       // ---- phase B: embed slice sg of image bE
       if (hasB) {
-        if (p.layernorm) {
-          if (tid == 0) {
-            const long long t0 = clock64();
-            while (ld_acquire_gpu(fp.done + bE) < fp.S * NW) {
-              __nanosleep(100);
-              if (clock64() - t0 > 4000000000LL) __trap();     // a broken schedule must fail the launch, never hang the GPU
-            }
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(FT) : "memory");
-          if (warp == 0) {
-            for (int l = 0; l < p.L; ++l) {
-              const double* st = fp.stats + (((long long)bE * p.L + l) * fp.S) * NW * 2;
-              double a = 0, c2 = 0;
-              for (int i = lane; i < fp.S * NW; i += 32) { a += __ldcg(st + 2 * i); c2 += __ldcg(st + 2 * i + 1); }
-              a = warp_sum(a);
-              c2 = warp_sum(c2);
-              const double n = (double)p.layers[l].C * p.layers[l].H * p.layers[l].W;
-              const double m = a / n;
-              double var = c2 / n - m * m;
-              if (var < 0) var = 0;
-              if (lane == 0) { s_mu[l] = (float)m; s_rs[l] = (float)(1.0 / sqrt(var + (double)p.eps)); }
-            }
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(FT) : "memory");
-        }
         const long long row0 = ((long long)bE * p.h0 + y) * p.w0;
         const bool yedge = (y == 0) || (y == p.h0 - 1);
         for (int l = 0; l < p.L; ++l) {
           const LayerDev& ly = p.layers[l];
-          const float mu = p.layernorm ? s_mu[l] : 0.f, rs = p.layernorm ? s_rs[l] : 1.f;
+          float mu = 0.f, rs = 1.f;
+          if (p.layernorm) {
+            const unsigned long long* mr = fp.murs + (long long)bE * p.L + l;
+            unsigned long long x = 0ull;
+            if (lane == 0) x = e_wait_set(mr, e_ld_relaxed_u64(mr));
+            x = __shfl_sync(0xffffffffu, x, 0);
+            mu = __uint_as_float((unsigned int)x);
+            rs = __uint_as_float((unsigned int)(x >> 32));
+          }
           const float nmr = -mu * rs;
           const float2 nmr2 = make_float2(nmr, nmr);
           // outputs of period tid at [tid * NOUT, + NOUT), of period tid + FT at FT * NOUT further
@@ -1408,7 +1499,9 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
                   const float2 f = __half22float2(h[i]);
                   nv2 = __ffma2_rn(f, f, nv2);
                 }
-                *reinterpret_cast<uint4*>(ph_ + half_ * (FT * NOUT) + o) = *reinterpret_cast<const uint4*>(h);
+                uint4* dst4 = reinterpret_cast<uint4*>(ph_ + half_ * (FT * NOUT) + o);
+                if (fp.cs) __stcs(dst4, *reinterpret_cast<const uint4*>(h));
+                else *dst4 = *reinterpret_cast<const uint4*>(h);
               }
               if constexpr (NOUT == 4) {
                 __align__(8) __half2 h[2];
@@ -1443,12 +1536,15 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
         }
       }
     }
-    if (!producer) asm volatile("bar.sync 1, %0;" ::"n"(FT) : "memory");      // s_nacc / s_mu are reused by the next item
+    if (!producer) asm volatile("bar.sync 1, %0;" ::"n"(FT) : "memory");      // s_nacc is reused by the next item
   }
 }
 
-__global__ void zero_words_kernel(unsigned int* __restrict__ dst, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = 0u;
+__global__ void init_words_kernel(unsigned int* __restrict__ ones, long long n_ones, unsigned int* __restrict__ zeros, long long n_zeros) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_ones + n_zeros; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_ones) ones[i] = 0xffffffffu;
+    else zeros[i - n_ones] = 0u;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1932,23 +2028,39 @@ static bool fused_eligible(const Plan& plan, const EmbedParams& p, const Periodi
 
 static constexpr size_t kZeroRowBytes = 4096;   // lean kernel: a row of zeros stands in for taps outside the map (<= 768 channels)
 
+static constexpr int kMinSeg = 4;   // shortest x segment the segment-length knob allows (sizes the statistics slots)
+
+// workspace of the fused kernels: [mean / rstd per (image, layer)] [statistics partials] [done[B], claim counter] [zero row]
+static size_t fused_murs_bytes(int L, int B) { return ((size_t)B * L * sizeof(unsigned long long) + 255) & ~(size_t)255; }
+static size_t fused_stats_bytes(int L, int B, int h0, int w0) {
+  // general kernel: one (sum, sum of squares) pair of doubles per slice; lean kernel: one packed 64-bit slot per slice and
+  // consumer warp (<= 4), slices as short as kMinSeg
+  const size_t S_gen = (size_t)h0 * ceil_div(w0, kMaxSeg), S_lean = (size_t)h0 * ceil_div(w0, kMinSeg);
+  return (std::max(S_gen * 2 * sizeof(double), S_lean * 4 * sizeof(unsigned long long)) * B * L + 255) & ~(size_t)255;
+}
+static size_t fused_ctr_bytes(int B) { return (((size_t)B + 64) * sizeof(int) + 255) & ~(size_t)255; }
 static size_t fused_ws_bytes(int L, int B, int h0, int w0) {
-  const int nxseg = ceil_div(w0, kMaxSeg);
-  const size_t S = (size_t)h0 * nxseg;
-  return (((size_t)B * L * S * 4 * 2 * sizeof(double) + 255) & ~(size_t)255) + ((((size_t)B + 64) * sizeof(int) + 255) & ~(size_t)255) +
-         kZeroRowBytes;    // statistics: one partial per slice (general kernel) or per slice and consumer warp (lean kernel, <= 4)
+  return fused_murs_bytes(L, B) + fused_stats_bytes(L, B, h0, w0) + fused_ctr_bytes(B) + kZeroRowBytes;
 }
 
 static int g_fused_lean = 1;      // debug knob (ac_debug_set key 9): 0 = always the general fused kernel
+static int g_fused_pd = 0;        // debug knob (key 10): lean kernel, claims the L2 prefetch of the statistics rows runs ahead (0 = off)
+static int g_fused_cs = 1;        // debug knob (key 11): lean kernel, operand rows stored with the streaming policy
+static int g_fused_l2pol = 1;     // debug knob (key 12): lean kernel, L2 policy of the map loads (0 normal, 1 evict_last, 2 evict_last / evict_first on last use)
+static int g_fused_seg = kMaxSeg; // debug knob (key 13): lean kernel, longest x segment of an item (kMinSeg .. kMaxSeg)
 
 static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, int num_sms, cudaStream_t st) {
   FusedParams fp;
   memset(&fp, 0, sizeof(fp));
-  p.nxseg = ceil_div(p.w0, kMaxSeg);
+  // lean kernel: fp16 operands + norms (+ fp32 Z), every consumer thread owns two periods of every layer
+  const bool lean_out = g_fused_lean && p.Zhi && !p.Zlo && p.op_dtype == AC_DT_F16 && n2 && pr.R == 1 && pr.A == 27 &&
+                        (p.ldz % 8 == 0) && (pr.ncols % 8 == 0) && (reinterpret_cast<uintptr_t>(p.Zhi) % 16 == 0) &&
+                        (!p.Z || reinterpret_cast<uintptr_t>(p.Z) % 16 == 0);
+  const int seg_max = lean_out ? g_fused_seg : kMaxSeg;
+  p.nxseg = ceil_div(p.w0, seg_max);
   p.xseg_len = ceil_div(p.w0, p.nxseg);
   p.nxseg = ceil_div(p.w0, p.xseg_len);
   p.b0 = 0;
-  fp.e = p;
   fp.n2 = n2;
   fp.S = p.h0 * p.nxseg;
   fp.LA = std::max(1, std::min(g_fused_la, p.B));
@@ -1956,20 +2068,23 @@ static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, 
   fp.gx = ceil_div(pr.nperiods, kFT * kPP);
   fp.t_stride = pr.ncols;
   fp.n_items = (long long)(p.B + fp.LA) * fp.S;
-  const size_t stats_b = ((size_t)p.B * p.L * fp.S * 4 * 2 * sizeof(double) + 255) & ~(size_t)255;
-  fp.stats = (double*)ws;
-  fp.done = (int*)((char*)ws + stats_b);
+  const size_t murs_b = fused_murs_bytes(p.L, p.B), stats_b = fused_stats_bytes(p.L, p.B, p.h0, p.w0), ctr_b = fused_ctr_bytes(p.B);
+  fp.murs = (unsigned long long*)ws;
+  fp.stats = (double*)((char*)ws + murs_b);
+  fp.done = (int*)((char*)ws + murs_b + stats_b);
   fp.counter = (unsigned int*)(fp.done + p.B);
-  // done[B], the claim counter and (after the 256-byte aligned counters) the zero row are cleared in one launch
-  const size_t ctr_b = (((size_t)p.B + 64) * sizeof(int) + 255) & ~(size_t)255;
   fp.zero_row = (const float*)((char*)fp.done + ctr_b);
-  const long long words = (long long)((ctr_b + kZeroRowBytes) / 4);
-  zero_words_kernel<<<(unsigned)std::min<long long>((words + 255) / 256, 64), 256, 0, st>>>((unsigned int*)fp.done, words);
+  fp.pd = g_fused_pd;
+  fp.cs = g_fused_cs;
+  fp.l2pol = g_fused_l2pol;
+  fp.e = p;
+  // one launch: mean / rstd and the lean kernel's statistics slots = all-ones ("unset", see kUnset); done[B], the claim counter
+  // and the zero row = 0
+  const long long ones = (long long)((murs_b + (lean_out ? (size_t)p.B * p.L * fp.S * 4 * sizeof(unsigned long long) : 0)) / 4);
+  const long long zeros = (long long)((ctr_b + kZeroRowBytes) / 4);
+  init_words_kernel<<<(unsigned)std::min<long long>((ones + zeros + 255) / 256, 296), 256, 0, st>>>((unsigned int*)ws, ones, (unsigned int*)fp.done,
+                                                                                                   zeros);
   AC_LAUNCH_CHECK();
-  // lean kernel: fp16 operands + norms (+ fp32 Z), every consumer thread owns two periods of every layer
-  const bool lean_out = g_fused_lean && p.Zhi && !p.Zlo && p.op_dtype == AC_DT_F16 && n2 && pr.R == 1 && pr.A == 27 &&
-                        (p.ldz % 8 == 0) && (pr.ncols % 8 == 0) && (reinterpret_cast<uintptr_t>(p.Zhi) % 16 == 0) &&
-                        (!p.Z || reinterpret_cast<uintptr_t>(p.Z) % 16 == 0);
 #define XL(b, ft)                                                                                                     \
   if (lean_out && pr.B == b && pr.nperiods == ft * kPP && p.layers[0].C == ft * kPP * 3) {                            \
     const size_t smem = ((size_t)kRingL * 3 * ft * kPP * 3 + (size_t)kMaxSeg * ft) * sizeof(float);                   \
@@ -2251,6 +2366,10 @@ extern "C" int ac_debug_set_fused(int key, int value) {
   if (key == 9 && (value == 0 || value == 1)) { g_fused_lean = value; return AC_OK; }
   if (key == 7 && value >= 1 && value <= 64) { g_fused_la = value; return AC_OK; }
   if (key == 8 && value >= 1 && value <= 3) { g_fused_cps = value; return AC_OK; }
+  if (key == 10 && value >= 0 && value <= 4096) { g_fused_pd = value; return AC_OK; }
+  if (key == 11 && (value == 0 || value == 1)) { g_fused_cs = value; return AC_OK; }
+  if (key == 12 && value >= 0 && value <= 2) { g_fused_l2pol = value; return AC_OK; }
+  if (key == 13 && value >= kMinSeg && value <= kMaxSeg) { g_fused_seg = value; return AC_OK; }
   return AC_ERR_INVALID;
 }
 

@@ -927,7 +927,7 @@ extern "C" int ac_debug_set(int key, int value) {
   if (key == 2) return ac_debug_set_embed(value);
   if (key == 5) return ac_debug_set_refine(value);
   if (key == 6) return ac_debug_set_refine_dot(value);
-  if (key == 7 || key == 8 || key == 9) return ac_debug_set_fused(key, value);
+  if (key >= 7 && key <= 13) return ac_debug_set_fused(key, value);
   if (key == 0 && (value == 1 || value == 2)) { g_tc_cta_group = value; return AC_OK; }
   if (key == 1 && value >= 1) { g_tc_gm = value; return AC_OK; }
   if (key == 3 && (value == 0 || value == 1)) { g_tc_l2hint = value; return AC_OK; }

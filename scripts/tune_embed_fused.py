@@ -1,6 +1,8 @@
-"""Fused single-pass embed (config-2 shape, 100 images): time per launch in isolation for the look-ahead / residency
-knobs, Z-free and with fp32 Z, against the per-layer launches of round 1 (variant 3) -- CUDA events, L2 flushed by the
+"""Fused single-pass embed (config-2 shape, 100 images): time per launch in isolation for the knobs of the lean kernel
+(look-ahead, L2 policy of the map loads, segment length, L2 prefetch distance, streaming stores), Z-free and with fp32 Z,
+against the per-layer launches of round 1 (variant 3) and the general fused kernel -- CUDA events, L2 flushed by the
 482 MB of maps themselves."""
+import itertools
 import os
 import sys
 
@@ -13,10 +15,23 @@ from anomaly_clustering_b200 import _lib, ops, pipeline, synth  # noqa: E402
 
 lib = _lib.load()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
 layers = [(768, 28, 28, True), (768, 28, 28, True)]
 feats, _ = synth.planted_features_device(range(n), layers, device="cuda")
 P, D = 784, 4096
 maps = sum(f[:, 1:].numel() * 4 for f in feats)
+DEFAULTS = {7: 2, 8: 3, 9: 1, 10: 0, 11: 1, 12: 1, 13: 16}
+NAMES = {7: "look-ahead", 10: "prefetch", 11: "streaming-stores", 12: "l2-policy", 13: "segment"}
+
+
+def setk(**kw):
+    for k, v in kw.items():
+        assert lib.ac_debug_set(int(k[1:]), int(v)) == 0, (k, v)
+
+
+def reset():
+    for k, v in DEFAULTS.items():
+        lib.ac_debug_set(k, v)
 
 
 def timed(want_z, reps=20):
@@ -32,27 +47,35 @@ def timed(want_z, reps=20):
     return e0.elapsed_time(e1) / reps
 
 
+def line(want_z, what, ms, nbytes):
+    print("want_z=%s  %s: %.3f ms  = %.0f GB/s algorithmic = %.3f of 6553.3" % (want_z, what, ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / 6553.3),
+          flush=True)
+
+
 for want_z in (False, True):
     nbytes = maps + n * P * D * 2 + n * P * 4 + (n * P * D * 4 if want_z else 0)
+    reset()
     lib.ac_debug_set(2, 3)
-    ms = timed(want_z)
-    print("want_z=%s  per-layer launches (+ statistics pass + row norms): %.3f ms  = %.0f GB/s algorithmic (%.1f MB)" % (want_z, ms, nbytes / ms / 1e6, nbytes / 1e6))
+    line(want_z, "per-layer launches (+ statistics pass + row norms) (%.1f MB)" % (nbytes / 1e6), timed(want_z), nbytes)
     lib.ac_debug_set(2, 0)
-    lib.ac_debug_set(9, 1)
-    for la in (1, 2, 4):
-        lib.ac_debug_set(7, la)
-        ms = timed(want_z)
-        print("want_z=%s  lean fused  look-ahead %d images: %.3f ms  = %.0f GB/s algorithmic = %.3f of 6547.8" % (
-            want_z, la, ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / 6547.8), flush=True)
-    lib.ac_debug_set(7, 2)
     lib.ac_debug_set(9, 0)
-    for cps in (3,):
-        for la in (1, 2, 3, 4, 8):
-            lib.ac_debug_set(7, la)
-            lib.ac_debug_set(8, cps)
-            ms = timed(want_z)
-            print("want_z=%s  fused  CTAs/SM %d  look-ahead %d images: %.3f ms  = %.0f GB/s algorithmic = %.3f of 6547.8" % (
-                want_z, cps, la, ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / 6547.8), flush=True)
-lib.ac_debug_set(7, 2)
-lib.ac_debug_set(8, 3)
-lib.ac_debug_set(9, 1)
+    line(want_z, "general fused kernel", timed(want_z), nbytes)
+    reset()
+    line(want_z, "lean fused, defaults %s" % DEFAULTS, timed(want_z), nbytes)
+    if quick:
+        continue
+    best = (1e9, None)
+    grid = itertools.product((2, 3, 4, 6, 8), (0, 1, 2), (16, 7)) if not want_z else itertools.product((2, 4), (0, 1), (16,))
+    for la, pol, seg in grid:
+        reset()
+        setk(k7=la, k12=pol, k13=seg)
+        ms = timed(want_z)
+        line(want_z, "lean fused  look-ahead %d  l2-policy %d  segment %2d" % (la, pol, seg), ms, nbytes)
+        if ms < best[0]:
+            best = (ms, (la, pol, seg))
+    la, pol, seg = best[1]
+    for pd, cs in ((0, 0), (37, 1), (148, 1)):
+        reset()
+        setk(k7=la, k12=pol, k13=seg, k10=pd, k11=cs)
+        line(want_z, "lean fused  look-ahead %d  l2-policy %d  segment %2d  prefetch %3d  streaming-stores %d" % (la, pol, seg, pd, cs), timed(want_z), nbytes)
+reset()

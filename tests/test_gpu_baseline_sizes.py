@@ -311,7 +311,8 @@ def test_config4_joint_bank_full_size_sampled_pairs_vs_oracle(config4):
     from anomaly_clustering_b200.distributed import pair_owned
 
     def d_gpu(i, j):          # query image i, bank image j
-        d2 = rowmin[j, i * P:(i + 1) * P] if pair_owned(i, j, n) else colmin[i, j * P:(j + 1) * P]
+        # both minima are indexed [other image, own patch row]: the owner j's tile wrote colmin[j, i*P + c] for the patches of i
+        d2 = (rowmin if pair_owned(i, j, n) else colmin)[j, i * P:(i + 1) * P]
         return d2.sqrt().cpu()
 
     for i, j in pairs:
@@ -325,7 +326,7 @@ def test_config4_joint_bank_full_size_sampled_pairs_vs_oracle(config4):
     own = (dd != 0) & ((2 * dd < n) | ((2 * dd == n) & (ii < jj)))                                     # [i, j], the kernel's rule
     assert all(bool(own[i, j]) == pair_owned(i, j, n) for i, j in pairs)
     rm = rowmin.reshape(n, n, P).permute(1, 0, 2)            # [i, j, P]: rowmin[j, i*P + p]
-    cm = colmin.reshape(n, n, P)                             # [i, j, P]
+    cm = colmin.reshape(n, n, P).permute(1, 0, 2)            # [i, j, P]: colmin[j, i*P + p], written by the owner j
     acc = torch.zeros(n, P, dtype=torch.float64, device="cuda")
     for j0 in range(0, n, 64):                               # chunks of bank images keep the temporaries small
         j1 = min(n, j0 + 64)
