@@ -1120,6 +1120,23 @@ __device__ __forceinline__ float e_lds32(uint32_t base) {
 __device__ __forceinline__ void e_mbar_wait_spin(uint32_t bar, uint32_t parity) {
   while (!e_mbar_try(bar, parity)) {}
 }
+// producer side of the lean kernel: a full ring means the consumers are several slots behind, so the single producer
+// thread sleeps between polls instead of burning issue slots of the scheduler it shares with three consumer warps
+// (round-2 capture: 25 % of all issued instructions were the producer's, most of them this loop)
+__device__ __forceinline__ void e_mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  if (e_mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!e_mbar_try(bar, parity)) {
+    __nanosleep(96);
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a broken pipeline must fail the launch, never hang the GPU
+  }
+}
+// acc + h * h with the product and the sum in fp32 (one FHFMA; the half is read straight from its half2 register)
+__device__ __forceinline__ float e_sq_acc(__half h, float acc) {
+  const unsigned short x = __half_as_ushort(h);
+  asm("fma.rn.f32.f16 %0, %1, %1, %0;" : "+f"(acc) : "h"(x));
+  return acc;
+}
 
 // one staged row of this thread: .x = channel c of its first period, .y = channel c of its second period, which lies
 // HALF floats further (periods tid and tid + FT): far enough apart that ptxas keeps the 32-bit loads apart and lets each
@@ -1236,7 +1253,7 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
   for (;;) {
     long long item;
     if (producer) {
-      e_mbar_wait(e_smem_u32(&s_qempty[qs]), qph ^ 1u);
+      e_mbar_wait_sleep(e_smem_u32(&s_qempty[qs]), qph ^ 1u);
       item = (long long)atomicAdd(fp.counter, 1u);
       s_items[qs] = item;
       asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(e_smem_u32(&s_qfull[qs])) : "memory");
@@ -1271,9 +1288,10 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
       const bool hasA = (bA >= 0) && p.layernorm, hasB = (bE >= 0);
       const uint32_t ring_u = e_smem_u32(ring);
       if (fp.pd > 0 && p.layernorm) {
-        // statistics rows of the item claimed fp.pd claims from now: DRAM -> L2 ahead of time, so that the statistics slots
-        // at the head of that item's in-order ring are L2 hits like its embed slots
-        const long long it2 = item + fp.pd;
+        // statistics rows of the item claimed fp.pd - 1 claims from now (1 = the item just claimed, whose first copies wait
+        // behind the ring slots of the previous item): DRAM -> L2 ahead of time, so that the statistics slots at the head of
+        // the item's in-order ring are L2 hits like its embed slots
+        const long long it2 = item + (fp.pd - 1);
         const int q2 = (int)(it2 / fp.S);
         if (q2 < p.B) {
           const int sg2 = (int)(it2 - (long long)q2 * fp.S);
@@ -1293,7 +1311,7 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
           const float* cur = ly.ptr + (long long)bA * ly.sb + (long long)y * ly.sh + (long long)xa * sw;
           int rem = npos;                                    // tokens left (>= 1 at every slot)
           for (int t = 0; t < nA; ++t, rem -= K, cur += K * sw) {
-            e_mbar_wait(empty0 + slot * 8, ph ^ 1u);
+            e_mbar_wait_sleep(empty0 + slot * 8, ph ^ 1u);
             const uint32_t fb = full0 + slot * 8, dst = ring_u + slot * kSlotBytes;
             e_mbar_expect_tx(fb, kSlotBytes);
 #pragma unroll
@@ -1313,7 +1331,7 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
           const float* r2 = r1 + ly.sh;
           const bool ok0 = (y >= 1), ok2 = (y + 1 < ly.H);
           for (int j = 0; j < ncols; ++j, r0 += sw, r1 += sw, r2 += sw) {
-            e_mbar_wait(empty0 + slot * 8, ph ^ 1u);
+            e_mbar_wait_sleep(empty0 + slot * 8, ph ^ 1u);
             const bool cin = (j != jlo) && (j != jhi);
             const uint32_t fb = full0 + slot * 8, dst = ring_u + slot * kSlotBytes;
             e_mbar_expect_tx(fb, kSlotBytes);
@@ -1496,8 +1514,8 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
                 for (int i = 0; i < 4; ++i) {
                   h[i] = half_ == 0 ? __floats2half2_rn(out[o + 2 * i].x, out[o + 2 * i + 1].x)
                                     : __floats2half2_rn(out[o + 2 * i].y, out[o + 2 * i + 1].y);
-                  const float2 f = __half22float2(h[i]);
-                  nv2 = __ffma2_rn(f, f, nv2);
+                  nv2.x = e_sq_acc(__low2half(h[i]), nv2.x);
+                  nv2.y = e_sq_acc(__high2half(h[i]), nv2.y);
                 }
                 uint4* dst4 = reinterpret_cast<uint4*>(ph_ + half_ * (FT * NOUT) + o);
                 if (fp.cs) __stcs(dst4, *reinterpret_cast<const uint4*>(h));
@@ -1508,8 +1526,8 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                   h[i] = half_ == 0 ? __floats2half2_rn(out[2 * i].x, out[2 * i + 1].x) : __floats2half2_rn(out[2 * i].y, out[2 * i + 1].y);
-                  const float2 f = __half22float2(h[i]);
-                  nv2 = __ffma2_rn(f, f, nv2);
+                  nv2.x = e_sq_acc(__low2half(h[i]), nv2.x);
+                  nv2.y = e_sq_acc(__high2half(h[i]), nv2.y);
                 }
                 *reinterpret_cast<uint2*>(ph_ + half_ * (FT * NOUT)) = *reinterpret_cast<const uint2*>(h);
               }
@@ -2044,7 +2062,7 @@ static size_t fused_ws_bytes(int L, int B, int h0, int w0) {
 }
 
 static int g_fused_lean = 1;      // debug knob (ac_debug_set key 9): 0 = always the general fused kernel
-static int g_fused_pd = 0;        // debug knob (key 10): lean kernel, claims the L2 prefetch of the statistics rows runs ahead (0 = off)
+static int g_fused_pd = 1;        // debug knob (key 10): lean kernel, L2 prefetch of the statistics rows: 0 = off, n = of the item n - 1 claims ahead
 static int g_fused_cs = 1;        // debug knob (key 11): lean kernel, operand rows stored with the streaming policy
 static int g_fused_l2pol = 1;     // debug knob (key 12): lean kernel, L2 policy of the map loads (0 normal, 1 evict_last, 2 evict_last / evict_first on last use)
 static int g_fused_seg = kMaxSeg; // debug knob (key 13): lean kernel, longest x segment of an item (kMinSeg .. kMaxSeg)

@@ -49,13 +49,14 @@ def _rows(ps: pipeline.PatchSet, i: int) -> pipeline.PatchSet:
     return pipeline.PatchSet(1, ps.P, ps.D, ps.grid, pick(ps.Z), pick(ps.hi), pick(ps.lo), pick(ps.n2))
 
 
-def _prec(precision, taus):
-    return pipeline.resolve_precision(precision or PRECISION, taus)
+def _prec(precision, taus, *Zs):
+    """auto -> mode for these taus, then the fp16 range guard on the caller's embeddings (pipeline.guard_operand_range)."""
+    return pipeline.guard_operand_range(pipeline.resolve_precision(precision or PRECISION, taus), *[torch.as_tensor(z) for z in Zs])
 
 
 def Weight_Distance_Unsupervised(Z, i, device, precision: Optional[str] = None):
     """utils.py:222-227 -> w_i [P]: mean over j != i of min_q ||Z[i,p] - Z[j,q]||."""
-    precision = _prec(precision, [0.1])     # tau unknown here: assume the most demanding one
+    precision = _prec(precision, [0.1], Z)     # tau unknown here: assume the most demanding one
     ps = _patchset(_to_device(Z, device), precision)
     q_self = torch.tensor([i], dtype=torch.int32, device=ps.Z.device)
     return pipeline.min_distance_weights(_rows(ps, i), ps, "unsupervised", precision, q_self=q_self)[0]
@@ -63,7 +64,7 @@ def Weight_Distance_Unsupervised(Z, i, device, precision: Optional[str] = None):
 
 def Weight_Distance_Supervised(Z, Z_train, i, device, precision: Optional[str] = None):
     """utils.py:230-237 -> w_i [P]: min over bank images and bank patches."""
-    precision = _prec(precision, [0.1])
+    precision = _prec(precision, [0.1], Z, Z_train)
     ps = _patchset(_to_device(Z, device), precision)
     bank = pipeline.patchset_from_Z(_to_device(Z_train, device), precision)
     return pipeline.min_distance_weights(_rows(ps, i), bank, "supervised", precision)[0]
@@ -77,7 +78,7 @@ def _alpha(w: torch.Tensor, tau: float) -> torch.Tensor:
 def Matrix_Alpha_Unsupervised(tau, k, Z, device, precision: Optional[str] = None):
     """utils.py:240-257 -> [N,P] float64 (k cancels in the normalisation, as in the reference)."""
     print("{:-^80}".format("Calculating Unsupervised Alpha Matrix"))
-    precision = _prec(precision, [tau])
+    precision = _prec(precision, [tau], Z)
     ps = _patchset(_to_device(Z, device), precision)
     return _alpha(pipeline.min_distance_weights(ps, ps, "unsupervised", precision), tau)
 
@@ -85,7 +86,7 @@ def Matrix_Alpha_Unsupervised(tau, k, Z, device, precision: Optional[str] = None
 def Matrix_Alpha_Supervised(tau, k, Z, Z_train, device, precision: Optional[str] = None):
     """utils.py:260-277 -> [N,P] float64."""
     print("{:-^80}".format("Calculating Supervised Alpha Matrix"))
-    precision = _prec(precision, [tau])
+    precision = _prec(precision, [tau], Z, Z_train)
     ps = _patchset(_to_device(Z, device), precision)
     bank = pipeline.patchset_from_Z(_to_device(Z_train, device), precision)
     return _alpha(pipeline.min_distance_weights(ps, bank, "supervised", precision), tau)

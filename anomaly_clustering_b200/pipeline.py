@@ -139,6 +139,35 @@ def embed_images(
     return PatchSet(n_img=N, P=P, D=target_dim, grid=(h, w), Z=Z, hi=hi, lo=lo, n2=n2)
 
 
+# element range inside which an arbitrary fp32 embedding may be rounded to fp16 operands: fp16 overflows at 65 504 and
+# loses relative precision below its normal range (6e-5); LayerNorm'd embeddings of this path are O(1)
+F16_OPERAND_RANGE = (2.0 ** -7, 2.0 ** 14)
+
+
+def guard_operand_range(precision: str, *tensors: torch.Tensor) -> str:
+    """Precision mode that is safe for embeddings that did NOT come out of this package's embed stage (the mirror
+    Matrix_Alpha_* / Weight_Distance_* accept any fp32 Z, like the reference's torch.cdist, utils.py:226).  Non-finite
+    values are refused; if the largest magnitude lies outside F16_OPERAND_RANGE the fp16 modes are replaced by the exact
+    fp32 kernel (slow, correct) with a warning instead of silently overflowing / flushing the operands."""
+    if precision == "f32":
+        return precision
+    fp16_mode = precision.startswith("f16")
+    lo, hi = F16_OPERAND_RANGE
+    for t in tensors:
+        if t is None or not t.numel():
+            continue
+        amax = float(t.detach().abs().amax())
+        if amax != amax or amax == float("inf"):
+            raise ValueError("embedding contains non-finite values")
+        if fp16_mode and amax > 0 and not (lo <= amax <= hi):
+            import warnings
+
+            warnings.warn("embedding magnitude %.3g is outside the fp16 operand range [%.3g, %.3g]: using the exact fp32 distance kernel "
+                          "(precision='f32'); rescale Z to O(1) for the tensor-core path" % (amax, lo, hi), RuntimeWarning, stacklevel=3)
+            return "f32"
+    return precision
+
+
 def patchset_from_Z(Z: torch.Tensor, precision: str = "f16") -> PatchSet:
     """Wrap an existing [N,P,D] fp32 embedding (e.g. the reference's `Z`) for the distance stage."""
     N, P, D = Z.shape

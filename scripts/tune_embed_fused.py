@@ -20,7 +20,7 @@ layers = [(768, 28, 28, True), (768, 28, 28, True)]
 feats, _ = synth.planted_features_device(range(n), layers, device="cuda")
 P, D = 784, 4096
 maps = sum(f[:, 1:].numel() * 4 for f in feats)
-DEFAULTS = {7: 2, 8: 3, 9: 1, 10: 0, 11: 1, 12: 1, 13: 16}
+DEFAULTS = {7: 2, 8: 3, 9: 1, 10: 1, 11: 1, 12: 1, 13: 16}
 NAMES = {7: "look-ahead", 10: "prefetch", 11: "streaming-stores", 12: "l2-policy", 13: "segment"}
 
 
@@ -64,18 +64,13 @@ for want_z in (False, True):
     line(want_z, "lean fused, defaults %s" % DEFAULTS, timed(want_z), nbytes)
     if quick:
         continue
-    best = (1e9, None)
-    grid = itertools.product((2, 3, 4, 6, 8), (0, 1, 2), (16, 7)) if not want_z else itertools.product((2, 4), (0, 1), (16,))
-    for la, pol, seg in grid:
+    grid = itertools.product((1, 2, 3, 4), (1, 2), (0, 1, 2)) if not want_z else itertools.product((1, 2), (1,), (0, 1))
+    for la, pol, pd in grid:
         reset()
-        setk(k7=la, k12=pol, k13=seg)
-        ms = timed(want_z)
-        line(want_z, "lean fused  look-ahead %d  l2-policy %d  segment %2d" % (la, pol, seg), ms, nbytes)
-        if ms < best[0]:
-            best = (ms, (la, pol, seg))
-    la, pol, seg = best[1]
-    for pd, cs in ((0, 0), (37, 1), (148, 1)):
+        setk(k7=la, k12=pol, k10=pd)
+        line(want_z, "lean fused  look-ahead %d  l2-policy %d  prefetch %d" % (la, pol, pd), timed(want_z), nbytes)
+    for seg, cs in ((14, 1), (10, 1), (16, 0)):
         reset()
-        setk(k7=la, k12=pol, k13=seg, k10=pd, k11=cs)
-        line(want_z, "lean fused  look-ahead %d  l2-policy %d  segment %2d  prefetch %3d  streaming-stores %d" % (la, pol, seg, pd, cs), timed(want_z), nbytes)
+        setk(k13=seg, k11=cs)
+        line(want_z, "lean fused  defaults but segment %2d  streaming-stores %d" % (seg, cs), timed(want_z), nbytes)
 reset()

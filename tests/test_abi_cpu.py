@@ -163,3 +163,23 @@ def test_mirror_surface_never_computes_on_cpu(lib_path):
     for call in calls:
         with pytest.raises(ValueError, match="CUDA tensors only"):
             call()
+
+
+def test_fp16_operand_range_guard_is_host_logic():
+    """pipeline.guard_operand_range: embeddings handed to the mirror from outside keep the requested tensor-core mode only
+    inside the fp16 operand range; outside they go to the exact fp32 kernel (with a warning), non-finite input is refused."""
+    import torch
+
+    from anomaly_clustering_b200 import pipeline
+
+    Z = torch.randn(2, 8, 16)
+    assert pipeline.guard_operand_range("f16", Z) == "f16"
+    assert pipeline.guard_operand_range("f16r", Z, None, Z * 100) == "f16r"
+    assert pipeline.guard_operand_range("f32", Z * 1e9) == "f32"
+    assert pipeline.guard_operand_range("bf16", Z * 1e9) == "bf16"          # bf16 has the fp32 exponent range
+    for scale in (1e6, 1e-6):
+        with pytest.warns(RuntimeWarning, match="fp16 operand range"):
+            assert pipeline.guard_operand_range("f16r", Z, Z * scale) == "f32"
+    assert pipeline.guard_operand_range("f16", torch.zeros(2, 3, 4)) == "f16"
+    with pytest.raises(ValueError, match="non-finite"):
+        pipeline.guard_operand_range("f16", torch.full((1, 2, 3), float("inf")))

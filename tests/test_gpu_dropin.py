@@ -56,6 +56,28 @@ def test_anomaly_clustering_core_wideresnet50_matches_oracle():
     assert (a_sup.cpu() - want_sup).abs().max().item() <= 1e-3
 
 
+def test_mirror_alpha_arbitrary_scale_embeddings_vs_oracle():
+    """The mirror Matrix_Alpha_* accepts ANY fp32 Z like the reference's torch.cdist (utils.py:226, :233): embeddings far
+    outside the fp16 range (x 1e6: fp16 operands would overflow; x 1e-6: they would flush to zero) take the exact fp32
+    kernel with a warning and still match the oracle to the alpha tolerance; non-finite input is refused."""
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(11)
+    Z1 = torch.randn(4, 64, 128, generator=gen)
+    for scale in (1e6, 1e-6):
+        Z = Z1 * scale
+        with pytest.warns(RuntimeWarning, match="fp16 operand range"):
+            a = utils.Matrix_Alpha_Unsupervised(scale, 1, Z, dev)
+        want = restated.matrix_alpha_unsupervised(scale, Z)
+        assert torch.isfinite(a).all() and (a.cpu() - want).abs().max().item() <= 1e-3
+        with pytest.warns(RuntimeWarning, match="fp16 operand range"):
+            a = utils.Matrix_Alpha_Supervised(2 * scale, 1, Z[:2], Z[2:], dev)
+        assert (a.cpu() - restated.matrix_alpha_supervised(2 * scale, Z[:2], Z[2:])).abs().max().item() <= 1e-3
+    bad = Z1.clone()
+    bad[1, 2, 3] = float("nan")
+    with pytest.raises(ValueError, match="non-finite"):
+        utils.Matrix_Alpha_Unsupervised(1.0, 1, bad, dev)
+
+
 def test_mirror_modules_standalone():
     dev = torch.device("cuda")
     gen = torch.Generator().manual_seed(2)
