@@ -739,7 +739,7 @@ struct FusedParams {
   unsigned long long* murs;  // [B][L] (mean, 1/std) packed as two floats, all-ones until the last statistics warp of the image wrote it (lean kernel)
   int pd;                  // lean kernel: items the L2 prefetch of the statistics rows runs ahead of the claims (0 = off)
   int cs;                  // lean kernel: operand rows stored with the streaming (evict-first) policy
-  int l2pol;               // lean kernel: L2 policy of the map loads: 0 normal, 1 evict_last, 2 evict_last except the last use of a row
+  int l2pol;               // lean kernel: L2 policy of the map loads: 0 normal, 1 evict_last
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -1123,11 +1123,21 @@ __device__ __forceinline__ void e_mbar_wait_spin(uint32_t bar, uint32_t parity) 
 // producer side of the lean kernel: a full ring means the consumers are several slots behind, so the single producer
 // thread sleeps between polls instead of burning issue slots of the scheduler it shares with three consumer warps
 // (round-2 capture: 25 % of all issued instructions were the producer's, most of them this loop)
+__device__ __forceinline__ bool e_mbar_try_suspend(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void e_mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   if (e_mbar_try(bar, parity)) return;
   const long long t0 = clock64();
-  while (!e_mbar_try(bar, parity)) {
-    __nanosleep(96);
+  while (!e_mbar_try_suspend(bar, parity, 2000u)) {   // suspended by the hardware until the phase flips (or the hint elapses)
     if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a broken pipeline must fail the launch, never hang the GPU
   }
 }
@@ -1189,11 +1199,12 @@ __device__ __forceinline__ void e_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
-static constexpr int kRingL = 7;         // ring depth of the lean kernel (72 KB of shared memory per CTA at 768 channels, 3 CTAs per SM)
+static constexpr int kRingL = 7;         // ring depth of the lean kernel (72 KB of shared memory per CTA at 768 channels, 3 CTAs per SM; a 5-slot ring
+                                         // at 4 CTAs per SM and 96 registers was measured 20 % slower: more images in flight than L2 holds)
 static constexpr int kItemQ = 2;         // items the producer may be ahead of the consumers
 
-template <int A, int B, int R, int FT, bool WZ>
-__global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast_kernel(const __grid_constant__ FusedParams fp) {
+template <int A, int B, int R, int FT, bool WZ, int RING, int MINB>
+__global__ void __launch_bounds__(FT + 32, MINB) embed_fused_fast_kernel(const __grid_constant__ FusedParams fp) {
   constexpr int K = 3;
   constexpr int CPP = A / (K * K);
   constexpr int NOUT = B / R;
@@ -1204,15 +1215,15 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
   static_assert(CPP == 3, "three channels per period (9C : Dp = 27 : B)");
   const EmbedParams& p = fp.e;
   extern __shared__ __align__(128) float smem_f[];
-  float* ring = smem_f;                                    // [kRingL][K][NCH]
-  float* s_nacc = smem_f + (size_t)kRingL * K * NCH;       // [kMaxSeg][FT] per-thread share of the row norms
-  __shared__ __align__(8) uint64_t s_full[kRingL], s_empty[kRingL];
+  float* ring = smem_f;                                    // [RING][K][NCH]
+  float* s_nacc = smem_f + (size_t)RING * K * NCH;       // [kMaxSeg][FT] per-thread share of the row norms
+  __shared__ __align__(8) uint64_t s_full[RING], s_empty[RING];
   __shared__ __align__(8) uint64_t s_qfull[kItemQ], s_qempty[kItemQ];
   __shared__ long long s_items[kItemQ];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = (warp == FT / 32);
   if (tid == 0) {
-    for (int i = 0; i < kRingL; ++i) {
+    for (int i = 0; i < RING; ++i) {
       e_mbar_init(e_smem_u32(&s_full[i]), 1);
       e_mbar_init(e_smem_u32(&s_empty[i]), FT / 32);
     }
@@ -1239,16 +1250,10 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
   if (producer && lane != 0) return;
   // L2 policies of the map loads: the maps must survive in L2 from their statistics read to their last embed read while
   // 1.3x their volume of operand rows streams out through the same cache
-  uint64_t pol_keep = 0, pol_last = 0;
+  uint64_t pol_keep = 0;
   if (producer) {
-    if (fp.l2pol == 0) {
-      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-      pol_last = pol_keep;
-    } else {
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-      pol_last = pol_keep;
-      if (fp.l2pol == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_last));
-    }
+    if (fp.l2pol == 0) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+    else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   }
   for (;;) {
     long long item;
@@ -1268,13 +1273,18 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
     }
     if (++qs == kItemQ) { qs = 0; qph ^= 1u; }
     if (item >= fp.n_items) break;
+    // Slice sg of an image (square patch grid, the host checks): for the STATISTICS it is a run of <= xseg_len tokens of one
+    // map row (yA, xaA ..), for the EMBEDDING it is one patch column x and the rows ya .. yb - 1.  The embed window slides
+    // DOWN a column because the K tokens (x-1, x, x+1) of a map row are contiguous in memory: a ring slot is ONE bulk copy
+    // of K tokens instead of K copies (the single producer thread pays ~30 instructions per copy).
     const int q = (int)(item / fp.S), sg = (int)(item - (long long)q * fp.S);
-    const int y = sg / p.nxseg, xs = sg - y * p.nxseg;
-    const int xa = xs * p.xseg_len, xb = min(p.w0, xa + p.xseg_len), npos = xb - xa;
+    const int s_hi = sg / p.nxseg, s_lo = sg - s_hi * p.nxseg;
+    const int yA = s_hi, xaA = s_lo * p.xseg_len, nposA = min(p.w0, xaA + p.xseg_len) - xaA;
+    const int x = s_hi, ya = s_lo * p.xseg_len, yb = min(p.h0, ya + p.xseg_len), npos = yb - ya;
     const int bA = (q < p.B) ? q : -1;                     // image whose statistics slice is reduced
     const int bE = q - fp.LA;                              // image whose slice is embedded (< 0: prologue item)
-    const int nA = (npos + K - 1) / K;                     // statistics slots: K tokens each (missing ones staged as zeros)
-    const int ncols = npos + K - 1;                        // embed slots: input columns xa-1 .. xb
+    const int nA = (nposA + K - 1) / K;                    // statistics slots: K tokens each (missing ones staged as zeros)
+    const int nrows = npos + K - 1;                        // embed slots: input rows ya-1 .. yb
 
     if (producer) {
       // ================================================================ producer thread: every slot is K full rows
@@ -1308,37 +1318,47 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
         for (int l = 0; l < p.L; ++l) {
           const LayerDev& ly = p.layers[l];
           const long long sw = ly.sw;
-          const float* cur = ly.ptr + (long long)bA * ly.sb + (long long)y * ly.sh + (long long)xa * sw;
-          int rem = npos;                                    // tokens left (>= 1 at every slot)
+          const bool contig = (sw == NCH);                   // K tokens = one copy
+          const float* cur = ly.ptr + (long long)bA * ly.sb + (long long)yA * ly.sh + (long long)xaA * sw;
+          int rem = nposA;                                   // tokens left (>= 1 at every slot)
           for (int t = 0; t < nA; ++t, rem -= K, cur += K * sw) {
             e_mbar_wait_sleep(empty0 + slot * 8, ph ^ 1u);
             const uint32_t fb = full0 + slot * 8, dst = ring_u + slot * kSlotBytes;
             e_mbar_expect_tx(fb, kSlotBytes);
+            if (contig && rem >= K) {
+              e_bulk_g2s_hint(dst, cur, kSlotBytes, fb, pol_keep);
+            } else {
 #pragma unroll
-            for (int ki = 0; ki < K; ++ki) e_bulk_g2s_hint(dst + ki * kRowBytes, (ki < rem) ? cur + ki * sw : fp.zero_row, kRowBytes, fb, pol_keep);
-            if (++slot == kRingL) { slot = 0; ph ^= 1u; }
+              for (int ki = 0; ki < K; ++ki) e_bulk_g2s_hint(dst + ki * kRowBytes, (ki < rem) ? cur + ki * sw : fp.zero_row, kRowBytes, fb, pol_keep);
+            }
+            if (++slot == RING) { slot = 0; ph ^= 1u; }
           }
         }
       }
       if (hasB) {
-        // column xa - 1 + j lies outside the map only at j == 0 of the first segment and at the last j of the last segment
-        const int jlo = (xa == 0) ? 0 : -1, jhi = (xb == p.w0) ? ncols - 1 : -1;
+        // map row ya - 1 + j lies outside the map only at j == 0 of the first segment and at the last j of the last segment
+        const int jlo = (ya == 0) ? 0 : -1, jhi = (yb == p.h0) ? nrows - 1 : -1;
+        const bool ok0 = (x >= 1), ok2 = (x + 1 < p.w0);
         for (int l = 0; l < p.L; ++l) {
           const LayerDev& ly = p.layers[l];
           const long long sw = ly.sw;
-          const float* r0 = ly.ptr + (long long)bE * ly.sb + (long long)(xa - 1) * sw + (long long)(y - 1) * ly.sh;
-          const float* r1 = r0 + ly.sh;
-          const float* r2 = r1 + ly.sh;
-          const bool ok0 = (y >= 1), ok2 = (y + 1 < ly.H);
-          for (int j = 0; j < ncols; ++j, r0 += sw, r1 += sw, r2 += sw) {
+          const bool one = ok0 && ok2 && (sw == NCH);        // the K tokens x-1 .. x+1 of a row: one copy
+          const float* r0 = ly.ptr + (long long)bE * ly.sb + (long long)(ya - 1) * ly.sh + (long long)(x - 1) * sw;
+          for (int j = 0; j < nrows; ++j, r0 += ly.sh) {
             e_mbar_wait_sleep(empty0 + slot * 8, ph ^ 1u);
-            const bool cin = (j != jlo) && (j != jhi);
+            const bool rin = (j != jlo) && (j != jhi);
             const uint32_t fb = full0 + slot * 8, dst = ring_u + slot * kSlotBytes;
             e_mbar_expect_tx(fb, kSlotBytes);
-            e_bulk_g2s_hint(dst, (cin && ok0) ? r0 : fp.zero_row, kRowBytes, fb, pol_last);
-            e_bulk_g2s_hint(dst + kRowBytes, cin ? r1 : fp.zero_row, kRowBytes, fb, pol_keep);
-            e_bulk_g2s_hint(dst + 2 * kRowBytes, (cin && ok2) ? r2 : fp.zero_row, kRowBytes, fb, pol_keep);
-            if (++slot == kRingL) { slot = 0; ph ^= 1u; }
+            if (!rin) {
+              e_bulk_g2s_hint(dst, fp.zero_row, kSlotBytes, fb, pol_keep);
+            } else if (one) {
+              e_bulk_g2s_hint(dst, r0, kSlotBytes, fb, pol_keep);
+            } else {
+              e_bulk_g2s_hint(dst, ok0 ? r0 : fp.zero_row, kRowBytes, fb, pol_keep);
+              e_bulk_g2s_hint(dst + kRowBytes, r0 + sw, kRowBytes, fb, pol_keep);
+              e_bulk_g2s_hint(dst + 2 * kRowBytes, ok2 ? r0 + 2 * sw : fp.zero_row, kRowBytes, fb, pol_keep);
+            }
+            if (++slot == RING) { slot = 0; ph ^= 1u; }
           }
         }
       }
@@ -1361,7 +1381,7 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
           }
         __syncwarp();
         if (lane == 0) e_mbar_arrive(empty0 + slot * 8);
-        if (++slot == kRingL) { slot = 0; ph ^= 1u; }
+        if (++slot == RING) { slot = 0; ph ^= 1u; }
       };
       // per-warp partial of layer l -> its slot in global memory (one 64-bit relaxed store, see kUnset)
       unsigned long long* part = reinterpret_cast<unsigned long long*>(fp.stats);
@@ -1400,9 +1420,9 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
               for (int u = 0; u < 8; ++u) {
                 const int i = i0 + u * 32 + lane;
                 if (i < n) {
-                  const unsigned long long x = e_wait_set(st + i, v[u]);
-                  a += (double)__uint_as_float((unsigned int)x);
-                  c2 += (double)__uint_as_float((unsigned int)(x >> 32));
+                  const unsigned long long pk = e_wait_set(st + i, v[u]);
+                  a += (double)__uint_as_float((unsigned int)pk);
+                  c2 += (double)__uint_as_float((unsigned int)(pk >> 32));
                 }
               }
             }
@@ -1418,36 +1438,38 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
       }
       // ---- phase B: embed slice sg of image bE
       if (hasB) {
-        const long long row0 = ((long long)bE * p.h0 + y) * p.w0;
-        const bool yedge = (y == 0) || (y == p.h0 - 1);
+        const long long row0 = ((long long)bE * p.h0 + ya) * p.w0 + x;      // first output row of the slice; the next is w0 further
+        const bool xedge = (x == 0) || (x == p.w0 - 1);
         for (int l = 0; l < p.L; ++l) {
           const LayerDev& ly = p.layers[l];
           float mu = 0.f, rs = 1.f;
           if (p.layernorm) {
             const unsigned long long* mr = fp.murs + (long long)bE * p.L + l;
-            unsigned long long x = 0ull;
-            if (lane == 0) x = e_wait_set(mr, e_ld_relaxed_u64(mr));
-            x = __shfl_sync(0xffffffffu, x, 0);
-            mu = __uint_as_float((unsigned int)x);
-            rs = __uint_as_float((unsigned int)(x >> 32));
+            unsigned long long pk = 0ull;
+            if (lane == 0) pk = e_wait_set(mr, e_ld_relaxed_u64(mr));
+            pk = __shfl_sync(0xffffffffu, pk, 0);
+            mu = __uint_as_float((unsigned int)pk);
+            rs = __uint_as_float((unsigned int)(pk >> 32));
           }
           const float nmr = -mu * rs;
           const float2 nmr2 = make_float2(nmr, nmr);
           // outputs of period tid at [tid * NOUT, + NOUT), of period tid + FT at FT * NOUT further
-          long long idx = (row0 + xa) * p.ldz + (long long)l * fp.t_stride + (long long)tid * NOUT;
-          float2 v[CPP][K][K];   // [channel][ki][physical column slot]; .x = first period, .y = second
+          long long idx = row0 * p.ldz + (long long)l * fp.t_stride + (long long)tid * NOUT;
+          const long long idx_step = (long long)p.w0 * p.ldz;
+          float2 v[CPP][K][K];   // [channel][physical row slot][kj]; .x = first period, .y = second
           float* na = s_nacc + tid;
           auto step = [&](auto rot_tag, int j) {
             constexpr int ROT = decltype(rot_tag)::value;
             constexpr int SLOT = (ROT + K - 1) % K;
             e_mbar_wait_spin(full0 + slot * 8, ph);
             const uint32_t base = ring_t + slot * kSlotBytes;
-            e_load_row3<0, NCH, FT * CPP>(base, v[0][0][SLOT], v[1][0][SLOT], v[2][0][SLOT]);
-            e_load_row3<1, NCH, FT * CPP>(base, v[0][1][SLOT], v[1][1][SLOT], v[2][1][SLOT]);
-            e_load_row3<2, NCH, FT * CPP>(base, v[0][2][SLOT], v[1][2][SLOT], v[2][2][SLOT]);
+            // the slot holds map row ya - 1 + j: tokens x-1, x, x+1 (kj = 0, 1, 2), NCH channels each
+            e_load_row3<0, NCH, FT * CPP>(base, v[0][SLOT][0], v[1][SLOT][0], v[2][SLOT][0]);
+            e_load_row3<1, NCH, FT * CPP>(base, v[0][SLOT][1], v[1][SLOT][1], v[2][SLOT][1]);
+            e_load_row3<2, NCH, FT * CPP>(base, v[0][SLOT][2], v[1][SLOT][2], v[2][SLOT][2]);
             __syncwarp();
             if (lane == 0) e_mbar_arrive(empty0 + slot * 8);
-            if (++slot == kRingL) { slot = 0; ph ^= 1u; }
+            if (++slot == RING) { slot = 0; ph ^= 1u; }
             if (j < K - 1) return;                         // the window is not full yet
             float2 out[NOUT];
 #pragma unroll
@@ -1457,17 +1479,17 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
               for (int jj = 0; jj < R; ++jj) {
                 const int r = o * R + jj;
                 const int f0 = (r * A) / B, f1 = ((r + 1) * A + B - 1) / B;
-                float2 sacc = v[f0 / (K * K)][(f0 % (K * K)) / K][((f0 % K) + ROT) % K];
+                float2 sacc = v[f0 / (K * K)][((f0 % (K * K)) / K + ROT) % K][f0 % K];
 #pragma unroll
                 for (int f = 0; f < A; ++f)
-                  if (f > f0 && f < f1) sacc = __fadd2_rn(sacc, v[f / (K * K)][(f % (K * K)) / K][((f % K) + ROT) % K]);
+                  if (f > f0 && f < f1) sacc = __fadd2_rn(sacc, v[f / (K * K)][((f % (K * K)) / K + ROT) % K][f % K]);
                 const float cf = rs * (1.0f / (float)(R * (f1 - f0)));
                 acc_o = __ffma2_rn(sacc, make_float2(cf, cf), acc_o);
               }
               out[o] = acc_o;
             }
-            const int x = xa + j - (K - 1);
-            if (yedge || x == 0 || x == p.w0 - 1) {          // warp-uniform, a few percent of the positions
+            const int y = ya + j - (K - 1);
+            if (xedge || y == 0 || y == p.h0 - 1) {          // warp-uniform, a few percent of the positions
               // taps outside the map were staged as zeros; the reference pads after the LayerNorm, i.e. they must count as
               // mu before the affine: add mu * rstd * (missing taps of the window) / (window size)
               float bad[K][K];
@@ -1535,12 +1557,12 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
             const float nv = nv2.x + nv2.y;
             *na = (l == 0) ? nv : (*na + nv);
             na += FT;
-            idx += p.ldz;
+            idx += idx_step;
           };
-          for (int j0 = 0; j0 < ncols; j0 += 3) {
+          for (int j0 = 0; j0 < nrows; j0 += 3) {
             step(std::integral_constant<int, 1>{}, j0);
-            if (j0 + 1 < ncols) step(std::integral_constant<int, 2>{}, j0 + 1);
-            if (j0 + 2 < ncols) step(std::integral_constant<int, 0>{}, j0 + 2);
+            if (j0 + 1 < nrows) step(std::integral_constant<int, 2>{}, j0 + 1);
+            if (j0 + 2 < nrows) step(std::integral_constant<int, 0>{}, j0 + 2);
           }
         }
         // squared norms of the operand rows of this segment: fixed summation order (bit-reproducible)
@@ -1550,7 +1572,7 @@ __global__ void __launch_bounds__(FT + 32, (FT == 128) ? 3 : 5) embed_fused_fast
 #pragma unroll
           for (int k2 = 0; k2 < FT / 32; ++k2) a += s_nacc[pos * FT + lane + 32 * k2];
           a = warp_sum(a);
-          if (lane == 0) fp.n2[row0 + xa + pos] = a;
+          if (lane == 0) fp.n2[row0 + (long long)pos * p.w0] = a;
         }
       }
     }
@@ -2044,7 +2066,7 @@ static bool fused_eligible(const Plan& plan, const EmbedParams& p, const Periodi
   return true;
 }
 
-static constexpr size_t kZeroRowBytes = 4096;   // lean kernel: a row of zeros stands in for taps outside the map (<= 768 channels)
+static constexpr size_t kZeroRowBytes = 12288;  // lean kernel: zeros that stand in for taps outside the map (one ring slot: 3 tokens x <= 768 channels)
 
 static constexpr int kMinSeg = 4;   // shortest x segment the segment-length knob allows (sizes the statistics slots)
 
@@ -2064,7 +2086,7 @@ static size_t fused_ws_bytes(int L, int B, int h0, int w0) {
 static int g_fused_lean = 1;      // debug knob (ac_debug_set key 9): 0 = always the general fused kernel
 static int g_fused_pd = 1;        // debug knob (key 10): lean kernel, L2 prefetch of the statistics rows: 0 = off, n = of the item n - 1 claims ahead
 static int g_fused_cs = 1;        // debug knob (key 11): lean kernel, operand rows stored with the streaming policy
-static int g_fused_l2pol = 1;     // debug knob (key 12): lean kernel, L2 policy of the map loads (0 normal, 1 evict_last, 2 evict_last / evict_first on last use)
+static int g_fused_l2pol = 1;     // debug knob (key 12): lean kernel, L2 policy of the map loads (0 normal, 1 evict_last)
 static int g_fused_seg = kMaxSeg; // debug knob (key 13): lean kernel, longest x segment of an item (kMinSeg .. kMaxSeg)
 
 static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, int num_sms, cudaStream_t st) {
@@ -2073,7 +2095,7 @@ static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, 
   // lean kernel: fp16 operands + norms (+ fp32 Z), every consumer thread owns two periods of every layer
   const bool lean_out = g_fused_lean && p.Zhi && !p.Zlo && p.op_dtype == AC_DT_F16 && n2 && pr.R == 1 && pr.A == 27 &&
                         (p.ldz % 8 == 0) && (pr.ncols % 8 == 0) && (reinterpret_cast<uintptr_t>(p.Zhi) % 16 == 0) &&
-                        (!p.Z || reinterpret_cast<uintptr_t>(p.Z) % 16 == 0);
+                        (!p.Z || reinterpret_cast<uintptr_t>(p.Z) % 16 == 0) && p.h0 == p.w0;   // slices: row runs / column runs
   const int seg_max = lean_out ? g_fused_seg : kMaxSeg;
   p.nxseg = ceil_div(p.w0, seg_max);
   p.xseg_len = ceil_div(p.w0, p.nxseg);
@@ -2103,25 +2125,23 @@ static int launch_fused(EmbedParams p, const Periodic& pr, float* n2, void* ws, 
   init_words_kernel<<<(unsigned)std::min<long long>((ones + zeros + 255) / 256, 296), 256, 0, st>>>((unsigned int*)ws, ones, (unsigned int*)fp.done,
                                                                                                    zeros);
   AC_LAUNCH_CHECK();
-#define XL(b, ft)                                                                                                     \
-  if (lean_out && pr.B == b && pr.nperiods == ft * kPP && p.layers[0].C == ft * kPP * 3) {                            \
-    const size_t smem = ((size_t)kRingL * 3 * ft * kPP * 3 + (size_t)kMaxSeg * ft) * sizeof(float);                   \
-    const int cps = (ft == 128) ? std::min(g_fused_cps, 3) : 5;                                                             \
-    const int grid_l = (int)std::min<long long>(fp.n_items, (long long)num_sms * cps);                                \
-    if (p.Z) {                                                                                                        \
-      auto kern = embed_fused_fast_kernel<27, b, 1, ft, true>;                                                        \
-      AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-      kern<<<grid_l, ft + 32, smem, st>>>(fp);                                                                        \
-    } else {                                                                                                          \
-      auto kern = embed_fused_fast_kernel<27, b, 1, ft, false>;                                                       \
-      AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-      kern<<<grid_l, ft + 32, smem, st>>>(fp);                                                                        \
-    }                                                                                                                 \
+#define XLK(b, ft, wz, ring, minb)                                                                                    \
+  {                                                                                                                   \
+    const size_t smem = ((size_t)ring * 3 * ft * kPP * 3 + (size_t)kMaxSeg * ft) * sizeof(float);                     \
+    const int grid_l = (int)std::min<long long>(fp.n_items, (long long)num_sms * std::min(g_fused_cps, minb));        \
+    auto kern = embed_fused_fast_kernel<27, b, 1, ft, wz, ring, minb>;                                                \
+    AC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+    kern<<<grid_l, ft + 32, smem, st>>>(fp);                                                                          \
     AC_LAUNCH_CHECK();                                                                                                \
     return AC_OK;                                                                                                     \
   }
+#define XL(b, ft)                                                                                                     \
+  if (lean_out && pr.B == b && pr.nperiods == ft * kPP && p.layers[0].C == ft * kPP * 3) {                            \
+    if (p.Z) XLK(b, ft, true, kRingL, (ft == 128 ? 3 : 5)) else XLK(b, ft, false, kRingL, (ft == 128 ? 3 : 5))        \
+  }
   XL(8, 128) XL(4, 128) XL(16, 64)
 #undef XL
+#undef XLK
   const int grid = (int)std::min<long long>(fp.n_items, (long long)num_sms * g_fused_cps);
 #define X(a, b, r)                                                                                                   \
   if (pr.A == a && pr.B == b && pr.R == r) {                                                                         \
@@ -2386,7 +2406,7 @@ extern "C" int ac_debug_set_fused(int key, int value) {
   if (key == 8 && value >= 1 && value <= 3) { g_fused_cps = value; return AC_OK; }
   if (key == 10 && value >= 0 && value <= 4096) { g_fused_pd = value; return AC_OK; }
   if (key == 11 && (value == 0 || value == 1)) { g_fused_cs = value; return AC_OK; }
-  if (key == 12 && value >= 0 && value <= 2) { g_fused_l2pol = value; return AC_OK; }
+  if (key == 12 && value >= 0 && value <= 1) { g_fused_l2pol = value; return AC_OK; }
   if (key == 13 && value >= kMinSeg && value <= kMaxSeg) { g_fused_seg = value; return AC_OK; }
   return AC_ERR_INVALID;
 }

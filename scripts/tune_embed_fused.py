@@ -64,13 +64,18 @@ for want_z in (False, True):
     line(want_z, "lean fused, defaults %s" % DEFAULTS, timed(want_z), nbytes)
     if quick:
         continue
-    grid = itertools.product((1, 2, 3, 4), (1, 2), (0, 1, 2)) if not want_z else itertools.product((1, 2), (1,), (0, 1))
+    grid = itertools.product((2, 3), (0, 1), (0, 1)) if not want_z else itertools.product((2,), (1,), (0, 1))
     for la, pol, pd in grid:
         reset()
         setk(k7=la, k12=pol, k10=pd)
         line(want_z, "lean fused  look-ahead %d  l2-policy %d  prefetch %d" % (la, pol, pd), timed(want_z), nbytes)
-    for seg, cs in ((14, 1), (10, 1), (16, 0)):
+    for cps in (2, 3):
+        reset()
+        setk(k8=cps)
+        line(want_z, "lean fused  CTAs/SM %d" % cps, timed(want_z), nbytes)
+    for seg, cs in ((16, 0),):
         reset()
         setk(k13=seg, k11=cs)
         line(want_z, "lean fused  defaults but segment %2d  streaming-stores %d" % (seg, cs), timed(want_z), nbytes)
+reset()
 reset()
