@@ -550,8 +550,10 @@ def main(argv=None):
 
     # ---------------------------------------------------------------- CPU baseline + oracle check (rank 0, N = 1)
     cpu_baseline = None
+    torch_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline, parity = cpu_baseline_leg(args, wl, pipeline, feats, bank, out, precision)
+        torch_gpu = torch_gpu_reference_leg(wl, pipeline, feats, bank, out)
 
     if rank == 0:
         value = n_img * args.steps / (elapsed_ms * 1e-3)
@@ -598,6 +600,7 @@ def main(argv=None):
                        "other_ms_per_step": elapsed_ms / args.steps - emb_ms - md_ms - refine_ms,
                        "comm_ms_per_step_rank0": comm},
             "cpu_baseline": cpu_baseline,
+            "reference_loop_on_gpu": torch_gpu,
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -701,6 +704,60 @@ def cpu_baseline_leg(args, wl, pipeline, feats, bank, out, precision):
         parity = {"check": "GPU w / alpha / X rows of %d query images against the CPU oracle (north_star tolerances)" % n_q,
                   "w_max_rel": e_w, "alpha_max_abs": e_a, "X_rel_l2": e_x, "ok": e_w <= 5e-4 and e_a <= 1e-3 and e_x <= 1e-3}
     return cpu_baseline, parity
+
+
+def torch_gpu_reference_leg(wl, pipeline, feats, bank, out, n_q=4):
+    """Reported next to the CPU baseline (rank 0, N = 1, untimed region): the reference's OWN distance loop -- one torch.cdist +
+    min(dim=1) per (query image, bank image), models/patchcore/utils.py:222-237 -- in plain torch fp32 on this GPU, which is
+    how upstream runs it when a GPU is present (examples/main.py:38 picks cuda:0).  A bounded sample of query images against
+    the whole bank; the embed stage and alpha / X are NOT charged to it (they are < 1 % of the reference's time), so the
+    images/s figure is an upper bound for the reference on this hardware.  Not an oracle, not a product path: a baseline."""
+    import torch
+
+    mode = wl["mode"]
+    if mode == "percategory":
+        n0 = wl["sizes"][0]
+        src_q = src_b = [f[:n0] for f in feats]                # first category
+    elif mode == "supervised":
+        src_q, src_b = feats, bank
+    else:
+        src_q = src_b = feats
+    qb = pipeline.embed_images(src_b, 3, 1, wl["Dp"], wl["D"], "f32", want_z=True)
+    Zb = qb.Z.reshape(qb.n_img, qb.P, qb.D)
+    if src_q is src_b:
+        Zq = Zb
+    else:
+        qq = pipeline.embed_images([f[:n_q] for f in src_q], 3, 1, wl["Dp"], wl["D"], "f32", want_z=True)
+        Zq = qq.Z.reshape(qq.n_img, qq.P, qq.D)
+    n_q = min(n_q, Zq.shape[0])
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False             # the reference's default: fp32 cdist
+
+    def loop(i):
+        mins = []
+        for j in range(Zb.shape[0]):
+            if mode != "supervised" and j == i:
+                continue
+            mins.append(torch.min(torch.cdist(Zq[i], Zb[j]), dim=1)[0].unsqueeze(1))
+        m = torch.cat(mins, dim=1)
+        return torch.min(m, dim=1)[0] if mode == "supervised" else torch.mean(m, dim=1)
+
+    try:
+        loop(0)                                                # warm-up (cuBLAS handles, autotuning)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ws = [loop(i) for i in range(n_q)]
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    ms = e0.elapsed_time(e1)
+    gw = out["w"][:n_q]
+    dev_w = float(((gw - torch.stack(ws)).abs() / torch.stack(ws).abs().clamp_min(1e-6)).max().item())
+    return {"value": n_q / (ms / 1e3), "unit": "images/s", "kind": "torch fp32 cdist loop of the reference on this GPU (distance stage only)",
+            "sample": "%d query images x %d bank images, %.1f ms" % (n_q, Zb.shape[0] - (0 if mode == "supervised" else 1), ms),
+            "w_max_rel_vs_ours": dev_w}
 
 
 if __name__ == "__main__":

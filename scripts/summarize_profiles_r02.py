@@ -109,10 +109,19 @@ for title, what, rep, key, notes in [
     ("Exact refine kernel (config 2, precision f16r)", "fp32 re-evaluation of the selected (query row, arg-min bank row) pairs",
      "r02_refine.ncu-rep", None,
      ["7.76 M pairs x one gathered 8 KB fp16 bank row: the kernel is bound by L2 -> SM traffic (see the L2 -> SM bytes row)."]),
-    ("Lean fused embed kernel (config 2, Z-free default)", "statistics + both layers + fp16 operands + norms in one persistent launch",
+    ("Lean fused embed kernel, FIRST version (call 10; config 2, Z-free default)", "statistics + both layers + fp16 operands + norms in one persistent launch",
      "r02_embed_lean.ncu-rep", None,
      ["Algorithmic bytes per launch: 482 MB of maps + 642 MB of operands + 0.3 MB of norms = 1 124 MB.  DRAM traffic above is "
-      "read + written; the excess over 1 124 MB is maps evicted from L2 between their statistics read and their embed reads."]),
+      "read + written; the excess over 1 124 MB is maps evicted from L2 between their statistics read and their embed reads.  "
+      "The source page of this capture showed the single producer thread as the bottleneck (188 instructions per ring slot, the "
+      "consumers waiting for data 23 % of their samples), the per-item re-reduction of the statistics behind two CTA barriers (11 %) "
+      "and the release fences (6 %) -- what calls 11-14 removed."]),
+    ("Lean fused embed kernel, FINAL version (call 14)", "hoisted + hardware-suspended producer, one bulk copy per ring slot (column walk), "
+     "last-arriver statistics with flag-free 64-bit slots, evict_last map loads, streaming operand stores, FHFMA norms",
+     "r02_embed_lean_v5.ncu-rep", None,
+     ["1 124 MB algorithmic in 254 us under the profiler (0.250-0.256 ms by CUDA events, isolated) = 0.67-0.685 of the 6 553 GB/s copy peak; "
+      "real DRAM traffic 1 248 MB = 4.9 TB/s = 0.75 of the peak.  No stall reason dominates any more (wait 26 %, long scoreboard 18 %, "
+      "selected 16 %); the kernel time scales with the SM clock (0.36-0.38 ms inside the bench step at 1.25-1.29 GHz)."]),
 ]:
     sec, d = section(title, what, rep, notes)
     md += sec
@@ -127,5 +136,10 @@ for title, what, rep, key, notes in [
             summary["mindist_tc_dram_bytes_per_launch"][key] = tot
 open(os.path.join(OUT, "r02_ncu_full.md"), "w").write("\n".join(md) + "\n")
 summary["launches"] = launches()
+if summary["launches"] is None:      # the launch list of call 10 is not in this directory: keep the digested one
+    try:
+        summary["launches"] = json.load(open(os.path.join(OUT, "ncu_summary.json"))).get("launches")
+    except Exception:
+        pass
 json.dump(summary, open(os.path.join(OUT, "ncu_summary.json"), "w"), indent=1)
 print(open(os.path.join(OUT, "r02_ncu_full.md")).read())
