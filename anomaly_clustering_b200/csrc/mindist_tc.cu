@@ -675,67 +675,103 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 // Device-side construction of the symmetric raster list.  (A host-built list needs an H2D copy, and
 // copy-engine work queues behind any large transfer the application has in flight -- measured: +9 ms
-// per launch while the next category's features were being uploaded.)  Single CTA: row r = (group, k)
-// of the raster, count its active query blocks, block-wide exclusive scan, then emit.
-__device__ __forceinline__ bool unit_has_work(const TcParams& p, int G, int mb, int img) {
-  int dw = img - p.win_begin;
-  if (dw < 0) dw += p.nb_img;
-  if (dw >= p.win_count) return false;          // bank image outside this launch's window
+// per launch while the next category's features were being uploaded.)
+static constexpr int kUnitTab = 4096;     // query blocks whose image range the unit builder tabulates in shared memory
+static constexpr int kUnitBlocks = 32;    // CTAs of the two unit-builder kernels (8 warps each)
+static constexpr int kUnitWarps = kUnitBlocks * 8;
+
+// Raster rows [ra, rb) of one warp: one lane per query block of the row's group, the activity mask of a row is a ballot.
+// The image range of every query block is tabulated in shared memory first, so the row loop carries no 64-bit division.
+// COUNT: returns the number of units of the run; otherwise emits them in raster order from position pos.
+template <bool COUNT>
+__device__ __forceinline__ long long walk_units(const TcParams& p, int G, int2* units, long long pos) {
+  __shared__ int s_i0[kUnitTab], s_i1[kUnitTab];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (tid >> 5), nw = gridDim.x * (blockDim.x >> 5);
   const long long rows_per_mb = (long long)kTileM * G;
-  const long long r0 = (long long)mb * rows_per_mb, r1 = min(p.Mq, r0 + rows_per_mb) - 1;
-  const int i0 = p.q_img0 + (int)(r0 / p.P), i1 = p.q_img0 + (int)(r1 / p.P);
-  for (int i = i0; i <= i1; ++i)
-    if (pair_owned_grouped(p.groups, i, img, p.nb_img)) return true;
-  return false;
+  const bool tab = p.n_mblocks <= kUnitTab;
+  auto mb_range = [&](int mb, int& i0, int& i1) {
+    const long long r0 = (long long)mb * rows_per_mb, r1 = min(p.Mq, r0 + rows_per_mb) - 1;
+    i0 = p.q_img0 + (int)(r0 / p.P);
+    i1 = p.q_img0 + (int)(r1 / p.P);
+  };
+  if (tab) {
+    for (int mb = tid; mb < p.n_mblocks; mb += blockDim.x) mb_range(mb, s_i0[mb], s_i1[mb]);
+  }
+  __syncthreads();
+  auto has_work = [&](int mb, int img) -> bool {
+    int dw = img - p.win_begin;
+    if (dw < 0) dw += p.nb_img;
+    if (dw >= p.win_count) return false;          // bank image outside this launch's window
+    int i0, i1;
+    if (tab) { i0 = s_i0[mb]; i1 = s_i1[mb]; } else mb_range(mb, i0, i1);
+    for (int i = i0; i <= i1; ++i)
+      if (pair_owned_grouped(p.groups, i, img, p.nb_img)) return true;
+    return false;
+  };
+  const int n_groups = (p.n_mblocks + p.GM - 1) / p.GM;
+  const long long rows = (long long)n_groups * p.KU;
+  // raster row = (group of GM query blocks, candidate bank image); the candidates of a group are walked circularly
+  // from the first image after the group's first query image (ownership looks forward in that order).
+  // A contiguous slice of rows per warp keeps the raster order.
+  const long long per = (rows + nw - 1) / nw;
+  const long long ra = min(rows, (long long)gw * per), rb = min(rows, ra + per);
+  long long cnt = 0;
+  if (ra < rb) {
+    int mg = (int)(ra / p.KU), k = (int)(ra - (long long)mg * p.KU);
+    for (long long r = ra; r < rb; ++r) {
+      const int gm_cur = min(p.GM, p.n_mblocks - mg * p.GM);
+      int ig, i1_;
+      if (tab) ig = s_i0[mg * p.GM]; else mb_range(mg * p.GM, ig, i1_);
+      int img = ig + 1 + k;                       // < 2 * nb_img
+      if (img >= p.nb_img) img -= p.nb_img;
+      if (img >= p.nb_img) img -= p.nb_img;
+      for (int m0 = 0; m0 < gm_cur; m0 += 32) {
+        const int mi = m0 + lane, mb = mg * p.GM + mi;
+        const bool act = (mi < gm_cur) && has_work(mb, img);
+        const unsigned mask = __ballot_sync(0xffffffffu, act);
+        if (COUNT) {
+          cnt += __popc(mask);
+        } else {
+          if (act) units[pos + __popc(mask & ((1u << lane) - 1u))] = make_int2(mb, img);
+          pos += __popc(mask);
+        }
+      }
+      if (++k == p.KU) { k = 0; ++mg; }
+    }
+  }
+  return cnt;
 }
 
-__global__ void __launch_bounds__(1024) build_units_kernel(TcParams p, int G, int2* units, long long* n_units, int* err_flag) {
-  __shared__ long long s_scan[1024];
-  const int tid = threadIdx.x;
-  if (tid == 0 && err_flag) {
+// Two small multi-CTA launches instead of one CTA (which needed 46 us -- 3 % of an 8-GPU config-2 step -- whichever way its
+// single SM was used): every warp counts the units of its run of raster rows, then every warp sums the counts of the runs
+// before its own (fixed order) and emits.
+__global__ void __launch_bounds__(256) count_units_kernel(TcParams p, int G, long long* warp_cnt, int* err_flag) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && err_flag) {
     *err_flag = 0;
     *reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(err_flag) + 128) = 0ull;   // dynamic-scheduler counter
   }
-  const int n_groups = (p.n_mblocks + p.GM - 1) / p.GM;
-  const long long rows = (long long)n_groups * p.KU;
-  const long long rows_per_mb = (long long)kTileM * G;
-  // raster row = (group of GM query blocks, candidate bank image); the candidates of a group are walked circularly
-  // from the first image after the group's first query image (ownership looks forward in that order)
-  auto row_info = [&](long long r, int& mg, int& img, int& gm_cur) {
-    mg = (int)(r / p.KU);
-    const int k = (int)(r - (long long)mg * p.KU);
-    gm_cur = min(p.GM, p.n_mblocks - mg * p.GM);
-    const int ig = p.q_img0 + (int)(((long long)mg * p.GM * rows_per_mb) / p.P);
-    img = (ig + 1 + k) % p.nb_img;
-  };
-  (void)rows_per_mb;
-  // contiguous slice of rows per thread keeps the raster order after the scan
-  const long long per = (rows + blockDim.x - 1) / blockDim.x;
-  const long long ra = min(rows, (long long)tid * per), rb = min(rows, ra + per);
-  long long cnt = 0;
-  for (long long r = ra; r < rb; ++r) {
-    int mg, img, gm_cur;
-    row_info(r, mg, img, gm_cur);
-    for (int mi = 0; mi < gm_cur; ++mi) cnt += unit_has_work(p, G, mg * p.GM + mi, img) ? 1 : 0;
+  const long long cnt = walk_units<true>(p, G, nullptr, 0);
+  if ((threadIdx.x & 31) == 0) warp_cnt[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = cnt;
+}
+
+__global__ void __launch_bounds__(256) emit_units_kernel(TcParams p, int G, const long long* __restrict__ warp_cnt, int2* units,
+                                                         long long* n_units) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+  long long before = 0, all = 0;
+  for (int w = lane; w < nw; w += 32) {
+    const long long c = warp_cnt[w];
+    all += c;
+    if (w < gw) before += c;
   }
-  s_scan[tid] = cnt;
-  __syncthreads();
-  for (int off = 1; off < (int)blockDim.x; off <<= 1) {   // Hillis-Steele inclusive scan
-    const long long v = (tid >= off) ? s_scan[tid - off] : 0;
-    __syncthreads();
-    s_scan[tid] += v;
-    __syncthreads();
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    before += __shfl_xor_sync(0xffffffffu, before, off);
+    all += __shfl_xor_sync(0xffffffffu, all, off);
   }
-  long long pos = s_scan[tid] - cnt;
-  if (tid == (int)blockDim.x - 1) *n_units = s_scan[tid];
-  for (long long r = ra; r < rb; ++r) {
-    int mg, img, gm_cur;
-    row_info(r, mg, img, gm_cur);
-    for (int mi = 0; mi < gm_cur; ++mi) {
-      const int mb = mg * p.GM + mi;
-      if (unit_has_work(p, G, mb, img)) units[pos++] = make_int2(mb, img);
-    }
-  }
+  if (gw == 0 && lane == 0) *n_units = all;
+  walk_units<false>(p, G, units, before);
 }
 
 // grid-stride fill (SM-side replacement of cudaMemsetAsync: keeps the launch sequence off the copy engines)
@@ -871,14 +907,17 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   if (sym) {
     // raster order: groups of GM query blocks; inside a group walk the bank images the group owns and,
     // per bank image, every block of the group that owns the pair (blocks sharing a bank image run
-    // together).  Built on the device (build_units_kernel).
+    // together).  Built on the device (count_units_kernel + emit_units_kernel).
     // a query block spans at most rows/P + 2 images, each owns at most half of its category (<= nb_img / 2 + 1 images)
     const long long span = ((long long)kTileM * G + P - 1) / P + 1;
     const long long max_units = (long long)prm.n_mblocks * std::min<long long>(nb_img, span * (nb_img / 2 + 1));
-    if (!unit_ws || unit_ws_bytes < 16 + (size_t)max_units * sizeof(int2)) return AC_ERR_WORKSPACE;
+    if (!unit_ws || unit_ws_bytes < 16 + (size_t)max_units * sizeof(int2) + kUnitWarps * sizeof(long long)) return AC_ERR_WORKSPACE;
     long long* d_n = (long long*)unit_ws;
     int2* d_units = (int2*)((char*)unit_ws + 16);
-    build_units_kernel<<<1, 1024, 0, st>>>(prm, G, d_units, d_n, err_flag);
+    long long* d_cnt = (long long*)((char*)unit_ws + 16 + (size_t)max_units * sizeof(int2));     // one count per builder warp
+    count_units_kernel<<<kUnitBlocks, 256, 0, st>>>(prm, G, d_cnt, err_flag);
+    AC_LAUNCH_CHECK();
+    emit_units_kernel<<<kUnitBlocks, 256, 0, st>>>(prm, G, d_cnt, d_units, d_n);
     AC_LAUNCH_CHECK();
     prm.units = d_units;
     prm.n_units = d_n;
@@ -1058,7 +1097,7 @@ extern "C" size_t ac_min_dist_workspace_bytes(int64_t Mq, int nb_img, int P, int
   const long long mblocks = (Mq + 127) / 128;
   const long long span = (256 + std::max(1, P) - 1) / std::max(1, P) + 1;
   const long long per_mb = std::min<long long>(nb_img, span * (nb_img / 2 + 1));
-  return 256 + 16 + (size_t)(mblocks * per_mb) * sizeof(int2);
+  return 256 + 16 + (size_t)(mblocks * per_mb) * sizeof(int2) + 4096;   // + the unit builder's per-warp counts
 }
 
 static int min_dist_impl(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,

@@ -24,6 +24,36 @@ static constexpr int kRQ = 4;            // query rows per block (fp32 in shared
 static constexpr int kWPR = 4;           // warps per query row: they take every kWPR-th bank image of the group
 static constexpr int kRefThreads = kRQ * kWPR * 32;
 
+// L2 policies: the gathered bank rows of a group (<= 96 MB) are re-read by every query chunk and must stay L2-resident while
+// the 16 KB fp32 query rows, the arg-min tables and the results stream through once per group (round-2 capture before the
+// hints: 28 GB of DRAM reads for 12.5 GB compulsory, L2 hit rate 47 %)
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ld_hint(const uint4* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+// (no L1::no_allocate here: a thread reads the two 16-byte halves of a 32-byte sector with two loads, and without L1 each
+// of them fetched the sector from L2 again -- measured +12 GB of L2 -> SM traffic)
+__device__ __forceinline__ float4 ld_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+
 __host__ __device__ inline bool pair_owned_r(int i, int j, int N) {   // same rule as mindist_tc.cu: pair_owned
   int d = j - i;
   if (d < 0) d += N;
@@ -66,8 +96,9 @@ template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& 
 // DOT: accumulate q.b (one FFMA per element) instead of (q-b)^2.
 template <typename T, int NIT, bool LO, bool DOT>
 __device__ __forceinline__ float row_dist2(const uint4* __restrict__ bh, const uint4* __restrict__ bl, const float4* qlo4,
-                                           const float4* qhi4, int G8, int lane) {
+                                           const float4* qhi4, int G8, int lane, uint64_t pol_keep) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float2 A = make_float2(0.f, 0.f), B = make_float2(0.f, 0.f);   // DOT: (a0, a1) and (a2, a3) as packed accumulators
   auto body = [&](const uint4& ub, int g) {
     float b[8];
     unpack8<T>(ub, b);
@@ -79,8 +110,11 @@ __device__ __forceinline__ float row_dist2(const uint4* __restrict__ bh, const u
     }
     const float4 ql = qlo4[g], qh = qhi4[g];
     if (DOT) {
-      a0 = fmaf(ql.x, b[0], a0); a1 = fmaf(ql.y, b[1], a1); a2 = fmaf(ql.z, b[2], a2); a3 = fmaf(ql.w, b[3], a3);
-      a0 = fmaf(qh.x, b[4], a0); a1 = fmaf(qh.y, b[5], a1); a2 = fmaf(qh.z, b[6], a2); a3 = fmaf(qh.w, b[7], a3);
+      // same four accumulation chains as the scalar form (bit-identical), two per packed fma.rn.f32x2
+      A = __ffma2_rn(make_float2(ql.x, ql.y), make_float2(b[0], b[1]), A);
+      B = __ffma2_rn(make_float2(ql.z, ql.w), make_float2(b[2], b[3]), B);
+      A = __ffma2_rn(make_float2(qh.x, qh.y), make_float2(b[4], b[5]), A);
+      B = __ffma2_rn(make_float2(qh.z, qh.w), make_float2(b[6], b[7]), B);
     } else {
       float d;
       d = ql.x - b[0]; a0 = fmaf(d, d, a0);
@@ -101,15 +135,16 @@ __device__ __forceinline__ float row_dist2(const uint4* __restrict__ bh, const u
     for (int it0 = 0; it0 < NIT; it0 += kBatch) {
       uint4 u[kBatch];
 #pragma unroll
-      for (int it = 0; it < kBatch; ++it) u[it] = __ldg(bh + lane + 32 * (it0 + it));
+      for (int it = 0; it < kBatch; ++it) u[it] = ld_hint(bh + lane + 32 * (it0 + it), pol_keep);
       asm volatile("" ::: "memory");
 #pragma unroll
       for (int it = 0; it < kBatch; ++it) body(u[it], lane + 32 * (it0 + it));
     }
   } else {
 #pragma unroll 4
-    for (int g = lane; g < G8; g += 32) body(__ldg(bh + g), g);
+    for (int g = lane; g < G8; g += 32) body(ld_hint(bh + g, pol_keep), g);
   }
+  if (DOT) return (A.x + A.y) + (B.x + B.y);
   return (a0 + a1) + (a2 + a3);
 }
 
@@ -123,6 +158,7 @@ __global__ void __launch_bounds__(kRefThreads, 2) refine_kernel(const RefinePara
   const int G8 = p.D >> 3;
   const long long m0 = (long long)blockIdx.x * kRQ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
   float qacc[kRQ];                                       // DOT: this lane's share of |q|^2 per staged row
 #pragma unroll
   for (int t = 0; t < kRQ; ++t) qacc[t] = 0.f;
@@ -138,7 +174,7 @@ __global__ void __launch_bounds__(kRefThreads, 2) refine_kernel(const RefinePara
       for (int i = 0; i < 8; ++i) f[i] = 0.f;
     } else if (p.Zq) {
       const float4* z = reinterpret_cast<const float4*>(p.Zq + r * p.D) + 2 * g;
-      const float4 a = __ldg(z), b = __ldg(z + 1);
+      const float4 a = ld_hint(z, pol_stream), b = ld_hint(z + 1, pol_stream);
       f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
     } else {
       unpack8<T>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.Qhi) + r * p.D) + g), f);
@@ -204,7 +240,7 @@ __global__ void __launch_bounds__(kRefThreads, 2) refine_kernel(const RefinePara
     c = __shfl_sync(0xffffffffu, c, 0);
     const uint4* bh = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.Bhi) + ((long long)j * p.P + c) * p.D);
     const uint4* bl = LO ? reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.Blo) + ((long long)j * p.P + c) * p.D) : nullptr;
-    float s = warp_sum(row_dist2<T, NIT, LO, DOT>(bh, bl, qlo4, qhi4, G8, lane));
+    float s = warp_sum(row_dist2<T, NIT, LO, DOT>(bh, bl, qlo4, qhi4, G8, lane, pol_keep));
     if (DOT) s = fmaxf(fmaf(-2.f, s, s_qn2[rr] + __ldg(p.Bn2 + (long long)j * p.P + c)), 0.f);
     if (lane == 0) p.dex[(long long)j * p.Mq + r] = sqrtf(s);
   }
@@ -236,7 +272,8 @@ static int dispatch_refine(const RefineParams& p, dim3 grid, size_t smem, cudaSt
 
 using namespace ac;
 
-static int g_refine_l2_mb = 96;   // debug knob (ac_debug_set key 5): bytes of bank operand rows one group keeps L2-resident
+static int g_refine_l2_mb = 128;  // debug knob (ac_debug_set key 5): bytes of bank operand rows one group keeps L2-resident (evict_last;
+                                  // measured at config 2 with the policy hints: 32 / 64 / 96 / 128 / 192 / 256 MB -> 14.7 / 11.6 / 11.8 / 10.3 / 10.8 / 10.8 ms)
 extern "C" int ac_debug_set_refine(int mb) {
   if (mb < 1 || mb > 512) return AC_ERR_INVALID;
   g_refine_l2_mb = mb;
@@ -267,9 +304,9 @@ extern "C" int ac_refine_min_dist(const float* Zq, const void* Qhi, const void* 
   p.rowarg = rowarg; p.colkey = (const unsigned long long*)colkey; p.sym = sym; p.q_img0 = q_img0; p.q_self = q_self; p.dex = dmin;
   p.groups = sym ? groups : nullptr;
   p.Bn2 = Bn2;
-  // bank images per group: their operand rows (96 MB by default, measured best on B200) stay L2-resident while every query chunk passes
+  // bank images per group: their operand rows (128 MB by default, measured best on B200) stay L2-resident while every query chunk passes
   const double img_bytes = (double)P * D * 2.0 * (Blo ? 2 : 1);
-  p.Jb = (int)std::max((double)kWPR, std::min(64.0, g_refine_l2_mb * 1.0e6 / img_bytes));
+  p.Jb = (int)std::max((double)kWPR, std::min(256.0, g_refine_l2_mb * 1.0e6 / img_bytes));
   p.Jb -= p.Jb % kWPR;                                             // the kWPR warps of a row take every kWPR-th image
   const long long chunks = (Mq + kRQ - 1) / kRQ;
   const int nbg = (nb_img + p.Jb - 1) / p.Jb;

@@ -84,7 +84,7 @@ def launches():
         a[1] += float(row["Metric Value"].replace(",", ""))
     tot = sum(a[1] for a in agg.values())
     md = ["# Launch list of 2 bench steps (config 2, N=1, Z-free default) -- `ncu --metrics gpu__time_duration.sum --clock-control none`",
-          "", "Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.  (Command: `scripts/r02_call17.sh`, final build of round 2.)", "",
+          "", "Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.  (Command: `scripts/r02_call20.sh`, final build of round 2.)", "",
           "| kernel | launches | total ms | avg us | share |", "|---|---:|---:|---:|---:|"]
     for k, a in agg.items():
         md.append("| `%s` | %d | %.3f | %.1f | %.1f %% |" % (k[:100], a[0], a[1] / 1e6, a[1] / a[0] / 1e3, 100 * a[1] / tot))
