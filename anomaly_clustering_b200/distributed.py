@@ -365,6 +365,7 @@ def run_path_sharded(
     pipeline._mark("gather_begin")
     pending = []
     pipeline_steps = None
+    symm_colmin = False
     # opt-in (AC_SHARD_PIPELINE=1): shard-granular pipeline -- multiply against shard k while shards k+1.. travel
     shard_pipeline = use_sym and getattr(compute, "supports_bank_window", False) and (
         symm_bank is not None or (world > 2 and os.environ.get("AC_SHARD_PIPELINE", "0") == "1" and not refined))
@@ -429,6 +430,18 @@ def run_path_sharded(
                 for src, reqs in pipeline_steps:
                     windows.append((None if src is None else (bounds[src][0], bounds[src][1] - bounds[src][0]), reqs))
             out, first = None, True
+            if symm_bank is not None and os.environ.get("AC_SYMM_COLMIN", "1") == "1":
+                # the column minima (keys in the refined modes) are written straight into symmetric memory; see
+                # SymmetricBank.exchange_colmin
+                n_max = max(b_ - a_ for a_, b_ in bounds)
+                Mq_l = q.n_img * P
+                rowmin_l = torch.empty(n_total, Mq_l, dtype=torch.float32, device=q.hi.device)
+                if refined:
+                    out = (rowmin_l, torch.zeros(n_total, Mq_l, dtype=torch.int32, device=q.hi.device),
+                           symm_bank.colmin_buffer(q.n_img, n_max, n_total * P, torch.int64))
+                else:
+                    out = (rowmin_l, symm_bank.colmin_buffer(q.n_img, n_max, n_total * P, torch.float32))
+                symm_colmin = True
             for window, reqs in windows:
                 for r in reqs:
                     r.wait()
@@ -458,7 +471,10 @@ def run_path_sharded(
             out = sym_launch(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision)
             pipeline._mark("mindist_end")
         pipeline._mark("exchange_begin")
-        colfull = exchange_colmin(out[-1], bounds, P, group)       # float minima, or (distance, row) keys when refined
+        if symm_colmin:
+            colfull = symm_bank.exchange_colmin(bounds, P, rank, world)
+        else:
+            colfull = exchange_colmin(out[-1], bounds, P, group)   # float minima, or (distance, row) keys when refined
         pipeline._mark("exchange_end")
         if refined:
             pipeline._mark("refine_begin")
