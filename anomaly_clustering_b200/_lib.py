@@ -110,6 +110,7 @@ SIGNATURES = {
          c_void_p],
     ),
     "ac_pairwise_l2": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ac_copy_blocks": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -313,3 +313,63 @@ extern "C" int ac_pairwise_l2(const float* X, int N, int D, float* Dmat, ac_stre
   AC_LAUNCH_CHECK();
   return AC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Batched strided 2-D copy (multi-GPU plumbing, no counterpart in the reference): up to 16 blocks of `rows` x `row_bytes` with
+// their own row strides in ONE launch.  The sharded path reads the column-minimum blocks of its query rows out of every
+// peer's symmetric-memory buffer with it (the sources are NVLink peer mappings; eight separate copy launches cost 64 us of
+// a 2.7 ms step at 8 GPUs).
+namespace ac {
+static constexpr int kMaxCopyBlocks = 16;
+struct CopyBlocks {
+  const char* src[kMaxCopyBlocks];
+  char* dst[kMaxCopyBlocks];
+  long long sstride[kMaxCopyBlocks], dstride[kMaxCopyBlocks], row_bytes[kMaxCopyBlocks];
+  int rows[kMaxCopyBlocks];
+};
+template <typename V>
+__global__ void __launch_bounds__(256) copy_blocks_kernel(const CopyBlocks p) {
+  const int b = blockIdx.y;
+  const long long per_row = p.row_bytes[b] / (long long)sizeof(V), total = per_row * p.rows[b];
+  const char* __restrict__ src = p.src[b];
+  char* __restrict__ dst = p.dst[b];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / per_row, c = i - r * per_row;
+    *reinterpret_cast<V*>(dst + r * p.dstride[b] + c * (long long)sizeof(V)) =
+        *reinterpret_cast<const V*>(src + r * p.sstride[b] + c * (long long)sizeof(V));
+  }
+}
+}  // namespace ac
+
+extern "C" int ac_copy_blocks(int n, const void* const* src_host, const int64_t* src_stride_bytes_host, void* const* dst_host,
+                              const int64_t* dst_stride_bytes_host, const int32_t* rows_host, const int64_t* row_bytes_host,
+                              ac_stream_t stream) {
+  if (n < 0 || n > ac::kMaxCopyBlocks) return AC_ERR_UNSUPPORTED;
+  if (n == 0) return AC_OK;
+  if (!src_host || !dst_host || !src_stride_bytes_host || !dst_stride_bytes_host || !rows_host || !row_bytes_host) return AC_ERR_INVALID;
+  int rc = check_device();
+  if (rc) return rc;
+  ac::CopyBlocks p;
+  memset(&p, 0, sizeof(p));
+  bool v16 = true;
+  long long most = 0;
+  for (int b = 0; b < n; ++b) {
+    if (!src_host[b] || !dst_host[b] || rows_host[b] < 0 || row_bytes_host[b] < 0 || row_bytes_host[b] % 4 != 0) return AC_ERR_INVALID;
+    p.src[b] = (const char*)src_host[b];
+    p.dst[b] = (char*)dst_host[b];
+    p.sstride[b] = src_stride_bytes_host[b];
+    p.dstride[b] = dst_stride_bytes_host[b];
+    p.rows[b] = rows_host[b];
+    p.row_bytes[b] = row_bytes_host[b];
+    v16 = v16 && ((reinterpret_cast<uintptr_t>(src_host[b]) | reinterpret_cast<uintptr_t>(dst_host[b]) | (uintptr_t)p.sstride[b] |
+                   (uintptr_t)p.dstride[b] | (uintptr_t)p.row_bytes[b]) % 16 == 0);
+    most = std::max(most, (long long)rows_host[b] * row_bytes_host[b]);
+  }
+  if (most == 0) return AC_OK;
+  const long long elems = most / (v16 ? 16 : 4);
+  dim3 grid((unsigned)std::min<long long>((elems + 255) / 256, 148LL * 2), (unsigned)n);
+  if (v16) ac::copy_blocks_kernel<uint4><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else ac::copy_blocks_kernel<unsigned int><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  AC_LAUNCH_CHECK();
+  return AC_OK;
+}

@@ -402,3 +402,27 @@ def pairwise_l2(X: torch.Tensor) -> torch.Tensor:
     out = torch.empty(N, N, dtype=torch.float32, device=X.device)
     check(lib.ac_pairwise_l2(_ptr(X), N, D, _ptr(out), _stream()), "ac_pairwise_l2")
     return out
+
+
+def copy_blocks(dsts: Sequence[torch.Tensor], srcs: Sequence[torch.Tensor]) -> None:
+    """dsts[k].copy_(srcs[k]) for up to 16 two-dimensional blocks (unit stride along the last axis, any row stride) in ONE
+    launch -- ac_copy_blocks.  The sources may be peer mappings of symmetric memory."""
+    import ctypes
+
+    lib = _lib.load()
+    n = len(dsts)
+    assert n == len(srcs) and n <= 16
+    if n == 0:
+        return
+    _need_cuda(*dsts)
+    _need_cuda(*srcs)
+    for d, s_ in zip(dsts, srcs):
+        assert d.dim() == 2 and d.shape == s_.shape and d.dtype == s_.dtype and d.stride(1) == 1 and s_.stride(1) == 1
+    es = dsts[0].element_size()
+    src = (ctypes.c_void_p * n)(*[s_.data_ptr() for s_ in srcs])
+    dst = (ctypes.c_void_p * n)(*[d.data_ptr() for d in dsts])
+    sst = (ctypes.c_int64 * n)(*[s_.stride(0) * s_.element_size() for s_ in srcs])
+    dstr = (ctypes.c_int64 * n)(*[d.stride(0) * d.element_size() for d in dsts])
+    rows = (ctypes.c_int32 * n)(*[d.shape[0] for d in dsts])
+    rb = (ctypes.c_int64 * n)(*[d.shape[1] * es for d in dsts])
+    check(lib.ac_copy_blocks(n, src, sst, dst, dstr, rows, rb, _stream()), "ac_copy_blocks")

@@ -149,6 +149,11 @@ class SymmetricBank:
                 peer = cur["peers"][src]
             dsts.append(out[sa:sb])
             srcs.append(peer[: sb - sa, a_r * P : b_r * P])
-        for d, s_ in zip(dsts, srcs):
-            d.copy_(s_, non_blocking=True)
+        if len(dsts) <= 16 and buf.element_size() % 4 == 0:
+            from . import ops
+
+            ops.copy_blocks(dsts, srcs)                   # one launch for all peers
+        else:
+            for d, s_ in zip(dsts, srcs):
+                d.copy_(s_, non_blocking=True)
         return out

@@ -237,6 +237,14 @@ int ac_weighted_embed_from_features(const ac_layer_t* layers_host, int L, int B,
                                     int D, int layernorm, float eps, const float* alpha, float* X, void* ws,
                                     size_t ws_bytes, ac_stream_t stream);
 
+/* Multi-GPU plumbing (no counterpart in the reference, which is single-device: examples/main.py:38): up to 16 strided 2-D blocks
+ * (rows x row_bytes, row_bytes a multiple of 4, own row strides in bytes) copied in ONE launch.  Sources / destinations may be
+ * peer mappings (symmetric memory over NVLink); the sharded path collects the column minima of its query rows with it.
+ * All array arguments are HOST arrays of length n. */
+int ac_copy_blocks(int n, const void* const* src_host, const int64_t* src_stride_bytes_host, void* const* dst_host,
+                   const int64_t* dst_stride_bytes_host, const int32_t* rows_host, const int64_t* row_bytes_host,
+                   ac_stream_t stream);
+
 /* Dmat[i,j] = || X[i] - X[j] ||_2, the Euclidean matrix Ward linkage consumes
  * (examples/test.py:193-195 -> scipy pdist).  Dmat [N,N] fp32, exactly symmetric, zero diagonal. */
 int ac_pairwise_l2(const float* X, int N, int D, float* Dmat, ac_stream_t stream);

@@ -87,6 +87,9 @@ def test_argument_validation_needs_no_gpu(lib_path):
     assert lib.ac_min_dist(None, None, None, 1, None, None, None, 1, 1, 8, 0, None, None, 0, None) == _lib.AC_ERR_INVALID
     assert lib.ac_embed(None, 1, 1, 3, 1, 8, 8, 1, 1e-5, None, None, None, 0, None, 0, None) == _lib.AC_ERR_INVALID
     assert lib.ac_debug_set(0, 7) == _lib.AC_ERR_INVALID
+    assert lib.ac_copy_blocks(1, None, None, None, None, None, None, None) == _lib.AC_ERR_INVALID
+    assert lib.ac_copy_blocks(17, None, None, None, None, None, None, None) == _lib.AC_ERR_UNSUPPORTED     # at most 16 blocks per launch
+    assert lib.ac_copy_blocks(0, None, None, None, None, None, None, None) == _lib.AC_OK
     if not torch.cuda.is_available():
         buf = (ctypes.c_float * 64)()
         rc = lib.ac_pairwise_l2(ctypes.cast(buf, ctypes.c_void_p), 4, 8, ctypes.cast(buf, ctypes.c_void_p), None)
