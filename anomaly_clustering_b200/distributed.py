@@ -452,6 +452,9 @@ def run_path_sharded(
                                  bank_window=window, init=first, out=out)
                 pipeline._mark("mindist_end")
                 first = False
+            if first and symm_colmin:
+                # this rank owns no pair at all (two images on two ranks): its peers still read its column minima -- "unset"
+                out[-1].view(torch.int32).fill_(0x7F7F7F7F)
         elif two_phase:
             # phase 1: bank images of the local shard (no remote data needed) overlaps the NCCL transfers
             pipeline._mark("mindist_begin")

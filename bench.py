@@ -471,6 +471,22 @@ def main(argv=None):
     op_bytes = 0 if precision == "f32" else (4 if precision in ("f16x3", "bf16x3") else 2)
     embed_bytes = n_embedded * (sum(c * h * w * 4 for c, h, w, _ in layers) + P * D * op_bytes + P * 4) + (0 if z_free else nq_local * P * D * 4)
     embed_gbs = embed_bytes / (emb_ms * 1e-3) / 1e9 if emb_ms > 0 else 0.0
+    # The same embed launch sequence timed ALONE (back to back, after an idle moment): inside a step it inherits the
+    # power-capped SM clock of the tensor kernel before it and its time scales with that clock
+    emb_iso_ms = None
+    if world == 1 and mode == "unsupervised" and feats is not None:
+        operand = "f32" if precision == "f32" else precision
+        torch.cuda.synchronize()
+        time.sleep(0.2)
+        for _ in range(3):
+            pipeline.embed_images(feats, 3, 1, Dp, D, operand, want_z=not z_free)
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for _ in range(20):
+            pipeline.embed_images(feats, 3, 1, Dp, D, operand, want_z=not z_free)
+        i1.record()
+        torch.cuda.synchronize()
+        emb_iso_ms = i0.elapsed_time(i1) / 20
 
     # ---------------------------------------------------------------- end-to-end (host buffers)
     e2e = None
@@ -596,6 +612,8 @@ def main(argv=None):
                          "algorithmic_flops_per_launch": flops, "algorithmic_tflops": alg_tflops, "traffic": traffic},
             "stages": {"embed_ms_per_step": emb_ms, "embed_bytes_per_step": embed_bytes, "embed_GBps": embed_gbs,
                        "embed_frac_of_hbm": embed_gbs / peaks["hbm_gbs"],
+                       "embed_isolated_ms": emb_iso_ms,
+                       "embed_isolated_frac_of_hbm": None if not emb_iso_ms else embed_bytes / (emb_iso_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                        "mindist_ms_per_step": md_ms, "refine_ms_per_step": refine_ms,
                        "other_ms_per_step": elapsed_ms / args.steps - emb_ms - md_ms - refine_ms,
                        "comm_ms_per_step_rank0": comm},
