@@ -72,6 +72,9 @@ struct __align__(64) TcParams {
   // groups[2*j], groups[2*j+1] = first image and image count of the category of bank image j; pairs exist only inside
   // a category and ownership is the circular rule inside it.  null = one category (all images).
   const int* groups;
+  // sharded runs: bank_ready[j] != 0 once bank image j (operand rows + norms) has landed in this GPU's memory; the producer
+  // waits for it before the first load of a unit.  null = the whole bank is resident.
+  const int* bank_ready;
   int* rowarg;                   // [nb_img, Mq] row inside bank image j that is nearest to query row r
   unsigned long long* colkey;    // sym: [nq_img, nb_img*P] (fp32 bits of d2 << 32) | row inside the query image, atomicMin target
 };
@@ -325,6 +328,24 @@ __device__ __forceinline__ unsigned long long warp_transpose_min_u64(unsigned lo
   return r[0];
 }
 
+// sharded runs (TcParams::bank_ready): spin until bank image img has landed; a flag that never comes kills the launch (code 7)
+__device__ __forceinline__ void wait_bank_ready(const TcParams& p, int img) {
+  const int* fl = p.bank_ready + img;
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+  if (v != 0) return;
+  const long long t0 = clock64();
+  do {
+    __nanosleep(200);
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+    if (v == 0 && clock64() - t0 > kWatchdogCycles) {
+      if (p.err) *p.err = 7;
+      __threadfence_system();
+      __trap();
+    }
+  } while (v == 0);
+}
+
 template <int G>
 __device__ __forceinline__ bool decode_unit(const TcParams& p, long long u, int& mb, int& img) {
   if (p.sym) {
@@ -442,6 +463,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
         if (u < 0) break;
         int mb, img;
         if (!decode_unit<G>(p, u, mb, img)) continue;
+        if (p.bank_ready) {
+          // the shard that holds this bank image may still be travelling (copy-engine pull on another stream): wait for its flag,
+          // then order the flag read before the TMA (async proxy) reads of the landed rows
+          wait_bank_ready(p, img);
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
         const int arow = mb * (kTileM * G) + (int)rank * kTileM;
         for (int t = 0; t < p.nt; ++t) {
           const bool last = (t == p.nt - 1);
@@ -535,6 +562,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
       if (u < 0) break;
       int mb, img;
       if (!decode_unit<G>(p, u, mb, img)) continue;
+      if (p.bank_ready) {
+        // the norms of this bank image are read below, ahead of the accumulator: they travel with the rows, wait for the flag too
+        if (lane == 0) wait_bank_ready(p, img);
+        __syncwarp();
+      }
       const long long row = (long long)mb * (kTileM * G) + rank * kTileM + et;
       const bool rvalid = row < p.Mq;
       // sym mode: this row contributes (row-min and column-min) only if its image owns the pair
@@ -556,7 +588,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mindist_tc_kernel(const __grid_
         const int cbase = t * p.wmain;
         const long long col0 = (long long)img * p.P + cbase;
         float* bn = s_bn2 + buf * kMaxN;
-        for (int c = eidx; c < width; c += 128) bn[c] = (c < valid) ? __ldg(p.bn2 + col0 + c) : INFINITY;
+        for (int c = eidx; c < width; c += 128) bn[c] = (c < valid) ? __ldcg(p.bn2 + col0 + c) : INFINITY;   // L2: may have landed during the launch
         asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(smem_u32(&tfull_bar[buf]), tphase, p.err, 4);
         tc_fence_after();
@@ -872,7 +904,7 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
                       const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int* err_flag, cudaStream_t st,
                       int sym = 0, int q_img0 = 0, unsigned int* colmin = nullptr, void* unit_ws = nullptr, size_t unit_ws_bytes = 0,
                       int win_begin = 0, int win_count = -1, int* rowarg = nullptr, unsigned long long* colkey = nullptr,
-                      const int* groups = nullptr) {
+                      const int* groups = nullptr, const int* bank_ready = nullptr) {
   const bool bf16 = (precision == AC_PREC_BF16 || precision == AC_PREC_BF16X3);
   const bool x3 = (precision == AC_PREC_F16X3 || precision == AC_PREC_BF16X3);
   if (D % 8 != 0) return AC_ERR_UNSUPPORTED;  // TMA needs a 16-byte row pitch
@@ -896,7 +928,7 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.dynamic = g_tc_dynamic;
   prm.counter = (unsigned long long*)((char*)err_flag + 128);   // inside the zeroed 256-byte workspace header
   prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin; prm.units = nullptr;
-  prm.rowarg = rowarg; prm.colkey = colkey; prm.groups = groups;
+  prm.rowarg = rowarg; prm.colkey = colkey; prm.groups = groups; prm.bank_ready = bank_ready;
   const bool arg = (rowarg != nullptr);
   if (arg && sym && !colkey) return AC_ERR_INVALID;
   prm.win_begin = win_begin; prm.win_count = (win_count < 0) ? nb_img : win_count;
@@ -1020,7 +1052,7 @@ __global__ void __launch_bounds__(256) reduce_weights_sym_kernel(const float* __
 static int min_dist_sym_impl(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
                              const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
                              int bank_count, int init_colmin, float* rowmin_d2, float* colmin_d2, int32_t* rowarg, uint64_t* colkey,
-                             const int32_t* groups, void* ws, size_t ws_bytes, ac_stream_t stream) {
+                             const int32_t* groups, void* ws, size_t ws_bytes, ac_stream_t stream, const int32_t* bank_ready = nullptr) {
   const bool arg = (rowarg != nullptr);
   if (!Qhi || !Bhi || !Qn2 || !Bn2 || !rowmin_d2 || (!arg && !colmin_d2) || (arg && !colkey) || Mq < 0 || nb_img < 1 || P < 1 ||
       D < 1 || q_img0 < 0)
@@ -1044,7 +1076,7 @@ static int min_dist_sym_impl(const void* Qhi, const void* Qlo, const float* Qn2,
   }
   return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, rowmin_d2, (int*)ws, st, 1, q_img0,
                            (unsigned int*)colmin_d2, (char*)ws + 256, ws_bytes - 256, bank_begin, bank_count, rowarg,
-                           (unsigned long long*)colkey, groups);
+                           (unsigned long long*)colkey, groups, bank_ready);
 }
 
 extern "C" int ac_min_dist_sym(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
@@ -1062,6 +1094,15 @@ extern "C" int ac_min_dist_sym_ex(const void* Qhi, const void* Qlo, const float*
   if ((rowarg != nullptr) != (colkey != nullptr)) return AC_ERR_INVALID;
   return min_dist_sym_impl(Qhi, Qlo, Qn2, Mq, q_img0, Bhi, Blo, Bn2, nb_img, P, D, precision, bank_begin, bank_count, init,
                            rowmin_d2, colmin_d2, rowarg, colkey, groups, ws, ws_bytes, stream);
+}
+
+extern "C" int ac_min_dist_sym_ready(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                                     const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                                     int bank_count, int init, float* rowmin_d2, float* colmin_d2, int32_t* rowarg, uint64_t* colkey,
+                                     const int32_t* groups, const int32_t* bank_ready, void* ws, size_t ws_bytes, ac_stream_t stream) {
+  if ((rowarg != nullptr) != (colkey != nullptr)) return AC_ERR_INVALID;
+  return min_dist_sym_impl(Qhi, Qlo, Qn2, Mq, q_img0, Bhi, Blo, Bn2, nb_img, P, D, precision, bank_begin, bank_count, init,
+                           rowmin_d2, colmin_d2, rowarg, colkey, groups, ws, ws_bytes, stream, bank_ready);
 }
 
 extern "C" int ac_min_dist_sym_arg(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,

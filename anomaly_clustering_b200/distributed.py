@@ -366,6 +366,7 @@ def run_path_sharded(
     pending = []
     pipeline_steps = None
     symm_colmin = False
+    ready_flags = None
     # opt-in (AC_SHARD_PIPELINE=1): shard-granular pipeline -- multiply against shard k while shards k+1.. travel
     shard_pipeline = use_sym and getattr(compute, "supports_bank_window", False) and (
         symm_bank is not None or (world > 2 and os.environ.get("AC_SHARD_PIPELINE", "0") == "1" and not refined))
@@ -376,7 +377,13 @@ def run_path_sharded(
         if symm_bank is not None:
             # every shard for the refined modes (each rank re-evaluates all of its rows against the whole bank)
             need_rank = [r for r in range(world) if r != rank] if refined else need_all[rank]
-            (hi_buf, lo_buf, n2_buf), pipeline_steps = symm_bank.publish_and_pull(bounds, P, need_rank, rank, world)
+            if os.environ.get("AC_SHARD_FLAGS", "1") == "1":
+                # ONE distance launch for the local and all remote bank images: its loader waits for per-image arrival flags
+                # that the side stream sets after each shard's pull (ac_min_dist_sym_ready) -- measured on one GPU with the
+                # launches of an 8-GPU config-2 rank: 2.40 ms in one launch against 2.59 ms in three windows
+                ready_flags = torch.zeros(n_total, dtype=torch.int32, device=q.hi.device)
+                ready_flags[lo_i:hi_i] = 1
+            (hi_buf, lo_buf, n2_buf), pipeline_steps = symm_bank.publish_and_pull(bounds, P, need_rank, rank, world, ready=ready_flags)
         else:
             (hi_buf, lo_buf, n2_buf), pipeline_steps = start_shard_pipeline([q.hi, q.lo, q.n2], bounds, P, need_all, group)
         bank = pipeline.PatchSet(n_total, P, q.D, q.grid, hi=hi_buf, lo=lo_buf, n2=n2_buf)
@@ -442,6 +449,18 @@ def run_path_sharded(
                 else:
                     out = (rowmin_l, symm_bank.colmin_buffer(q.n_img, n_max, n_total * P, torch.float32))
                 symm_colmin = True
+            if ready_flags is not None:
+                # flags mode: a single launch over the whole bank now; the pull events are awaited after it (refine and the
+                # next step's buffer reuse need them, the launch itself does not)
+                all_reqs = [r for _, reqs in windows for r in reqs]
+                windows = [(None, [])]
+                pipeline._mark("mindist_begin")
+                out = sym_launch(q.hi, q.lo, q.n2, lo_i, bank.hi, bank.lo, bank.n2, n_total, P, precision, init=True, out=out,
+                                 ready=ready_flags)
+                pipeline._mark("mindist_end")
+                first = False
+                for r in all_reqs:
+                    r.wait()
             for window, reqs in windows:
                 for r in reqs:
                     r.wait()

@@ -214,8 +214,15 @@ def min_dist(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, 
     return dmin
 
 
+def _ready_ok(ready: Optional[torch.Tensor], nb_img: int) -> None:
+    """bank_ready flags of ac_min_dist_sym_ready: one int32 per bank image on the device, or None (whole bank resident)."""
+    if ready is not None:
+        assert ready.is_cuda and ready.dtype == torch.int32 and ready.is_contiguous() and ready.numel() == nb_img
+
+
 def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str,
-                 bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None, groups: Optional[torch.Tensor] = None):
+                 bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None, groups: Optional[torch.Tensor] = None,
+                 ready: Optional[torch.Tensor] = None):
     """Symmetric self-bank form: (rowmin_d2 [nb_img, Mq], colmin_d2 [Mq/P, nb_img*P]) squared distances.
     bank_window=(begin, count) restricts the launch to a circular range of bank images; pass the previous
     call's result as `out` with init=False to accumulate a second window into the same buffers."""
@@ -233,9 +240,10 @@ def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int,
     ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
     _groups_ok(groups, nb_img)
-    rc = lib.ac_min_dist_sym_ex(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
-                                int(begin), int(count), int(bool(init)), _ptr(rowmin), _ptr(colmin), None, None, _ptr(groups),
-                                _ptr(ws), ws_bytes, _stream())
+    _ready_ok(ready, nb_img)
+    rc = lib.ac_min_dist_sym_ready(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
+                                   int(begin), int(count), int(bool(init)), _ptr(rowmin), _ptr(colmin), None, None, _ptr(groups),
+                                   _ptr(ready), _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_min_dist_sym")
     return rowmin, colmin
 
@@ -258,7 +266,8 @@ def min_dist_arg(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: s
 
 
 def min_dist_sym_arg(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str,
-                     bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None, groups: Optional[torch.Tensor] = None):
+                     bank_window: Optional[Tuple[int, int]] = None, init: bool = True, out=None, groups: Optional[torch.Tensor] = None,
+                     ready: Optional[torch.Tensor] = None):
     """ac_min_dist_sym_arg: (rowmin_d2 [nb_img, Mq], rowarg [nb_img, Mq] int32, colkey [Mq/P, nb_img*P] int64 =
     (fp32 bits of the column minimum << 32) | row inside the query image).  Windows / accumulation as min_dist_sym."""
     lib = _lib.load()
@@ -276,9 +285,10 @@ def min_dist_sym_arg(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: 
     ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
     _groups_ok(groups, nb_img)
-    rc = lib.ac_min_dist_sym_ex(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
-                                int(begin), int(count), int(bool(init)), _ptr(rowmin), None, _ptr(rowarg), _ptr(colkey),
-                                _ptr(groups), _ptr(ws), ws_bytes, _stream())
+    _ready_ok(ready, nb_img)
+    rc = lib.ac_min_dist_sym_ready(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, q_img0, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec,
+                                   int(begin), int(count), int(bool(init)), _ptr(rowmin), None, _ptr(rowarg), _ptr(colkey),
+                                   _ptr(groups), _ptr(ready), _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_min_dist_sym_arg")
     return rowmin, rowarg, colkey
 

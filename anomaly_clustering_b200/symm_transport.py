@@ -78,9 +78,12 @@ class SymmetricBank:
             cur["peers"][key] = cur["handles"][which].get_buffer(src, tuple(buf.shape), buf.dtype)
         return cur["peers"][key]
 
-    def publish_and_pull(self, bounds: Sequence[Tuple[int, int]], P: int, need_rank: Sequence[int], rank: int, world: int):
+    def publish_and_pull(self, bounds: Sequence[Tuple[int, int]], P: int, need_rank: Sequence[int], rank: int, world: int,
+                         ready: Optional[torch.Tensor] = None):
         """After the local slices were written on the current stream: barrier, then pull the shards of `need_rank`.
-        Returns ((hi_buf, lo_buf, n2_buf), [(source rank, [request]), ...]) in arrival (ring) order."""
+        Returns ((hi_buf, lo_buf, n2_buf), [(source rank, [request]), ...]) in arrival (ring) order.
+        ready [n_total] int32 (zeroed by the caller on the current stream): the flags of a shard's images are set to 1 on the
+        side stream right after its copies -- the arrival flags of ac_min_dist_sym_ready."""
         cur = self.sets[self.step & 1]
         self.step += 1
         main = torch.cuda.current_stream()
@@ -100,6 +103,8 @@ class SymmetricBank:
                         continue
                     peer = self._peer(cur, which, src)
                     buf[sa * P : sb * P].copy_(peer[sa * P : sb * P], non_blocking=True)
+                if ready is not None:
+                    ready[sa:sb].fill_(1)
                 ev = torch.cuda.Event()
                 ev.record(self.side)
                 steps.append((src, [_EventRequest(ev)]))

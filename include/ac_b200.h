@@ -209,6 +209,16 @@ int ac_min_dist_sym_ex(const void* Qhi, const void* Qlo, const float* Qn2, int64
                        const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
                        int bank_count, int init, float* rowmin_d2, float* colmin_d2, int32_t* rowarg, uint64_t* colkey,
                        const int32_t* groups, void* ws, size_t ws_bytes, ac_stream_t stream);
+
+/* The same launch for a bank that is still ARRIVING (sharded runs: remote shards are pulled by the copy engines while the kernel
+ * runs): bank_ready [nb_img] int32 in device memory, bank_ready[j] != 0 once the operand rows and norms of bank image j have
+ * landed (written by whatever stream performs the transfer, after it); the kernel's loader waits for the flag of a bank image
+ * before its first load of it (watchdog code 7 if it never comes).  NULL = ac_min_dist_sym_ex.  One launch then covers the
+ * local and all remote bank images instead of one launch per landed window. */
+int ac_min_dist_sym_ready(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
+                          const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
+                          int bank_count, int init, float* rowmin_d2, float* colmin_d2, int32_t* rowarg, uint64_t* colkey,
+                          const int32_t* groups, const int32_t* bank_ready, void* ws, size_t ws_bytes, ac_stream_t stream);
 int ac_reduce_weights_sym_ex(const float* rowmin_d2, const float* colmin_d2, int64_t Mq, int nb_img, int Pq, int q_img0,
                              const int32_t* groups, float* w, ac_stream_t stream);
 int ac_reduce_weights_ex(const float* dmin, int64_t Mq, int nb_img, int Pq, const int32_t* q_self, const int32_t* groups,

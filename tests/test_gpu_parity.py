@@ -304,6 +304,45 @@ def test_mindist_symmetric_equals_all_pairs(n, P, D, precision):
     assert ((w_sym.double().cpu() - want).abs() / want).max().item() <= 5e-4
 
 
+@pytest.mark.parametrize("arg", [False, True])
+def test_mindist_symmetric_waits_for_arriving_bank(arg):
+    """ac_min_dist_sym_ready (one launch over a bank whose remote shards are still travelling): the query slice and its own
+    bank images are resident, the other images' rows and norms are copied in by ANOTHER stream long after the kernel has
+    started, which then sets their arrival flags.  The result must be the one of the resident bank -- bit for bit."""
+    n, P, D, nq = 9, 96, 256, 3
+    gen = torch.Generator().manual_seed(17)
+    Z = (torch.randn(1, P, D, generator=gen) + 0.5 * torch.randn(n, P, D, generator=gen)).cuda()
+    ps = pipeline.patchset_from_Z(Z, "f16")
+    launch = ops.min_dist_sym_arg if arg else ops.min_dist_sym
+    sl = slice(0, nq * P)
+    want = launch(ps.hi[sl], None, ps.n2[sl], 0, ps.hi, None, ps.n2, n, P, "f16")
+    torch.cuda.synchronize()
+    hi = torch.full_like(ps.hi, float("nan"))                 # remote rows: poison until they "arrive"
+    n2 = torch.full_like(ps.n2, float("nan"))
+    hi[sl], n2[sl] = ps.hi[sl], ps.n2[sl]
+    ready = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ready[:nq] = 1
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for a in range(nq, n, 2):                             # "shards" of two images, ~10 ms apart
+            b = min(n, a + 2)
+            torch.cuda._sleep(int(2.0e7))
+            hi[a * P : b * P].copy_(ps.hi[a * P : b * P], non_blocking=True)
+            n2[a * P : b * P].copy_(ps.n2[a * P : b * P], non_blocking=True)
+            ready[a:b].fill_(1)
+    got = launch(hi[sl], None, n2[sl], 0, hi, None, n2, n, P, "f16", ready=ready)     # starts at once on the current stream
+    torch.cuda.synchronize()
+    # rowmin [n, nq*P] is written only for the pairs the query image owns (the rest is uninitialised memory by contract)
+    from anomaly_clustering_b200.distributed import pair_owned
+
+    own = torch.tensor([[pair_owned(i, j, n) for i in range(nq)] for j in range(n)], device="cuda")      # [j, i]
+    mask = own[:, :, None].expand(n, nq, P).reshape(n, nq * P)
+    assert mask.any() and torch.equal(got[0][mask], want[0][mask]) and torch.isfinite(got[0][mask]).all()
+    for g, w_ in zip(got[1:], want[1:]):                      # column minima / keys (initialised everywhere), row arg-mins
+        assert torch.equal(g, w_)
+
+
 def test_mindist_symmetric_sharded_slices():
     """Two query slices of one bank (what two ranks compute) + the column-block exchange reproduce the
     single-slice result."""
