@@ -2,10 +2,22 @@
 
 w_i, alpha_i and X_i depend only on query image i and the read-only bank
 (reference: models/patchcore/utils.py:245-246, 265-266 -- the loop over i is independent), so:
-  rank r embeds its slice of images  ->  all-gather of the tensor-core operands (+ norms): every
-  rank holds the whole bank  ->  rank r runs stages 2/3 for its query slice  ->  all-gather of the
-  X rows  ->  Dmat.  fp32 Z never leaves its rank.  The only collectives are the two gathers.
-On CPU (gloo) the same sharding / gather logic is exercised by tests with a stand-in compute."""
+  rank r embeds its slice of images  ->  the tensor-core operands (+ norms) of the bank images whose pairs it owns travel to
+  it  ->  rank r runs stages 2/3 for its query slice (symmetric form: every unordered image pair once, the column minima of
+  other ranks' query rows are exchanged)  ->  all-gather of the X rows  ->  Dmat.  fp32 Z never leaves its rank.
+On CPU (gloo) the same sharding / gather logic is exercised by tests with a stand-in compute.
+
+Schedules of the symmetric sharded path; the default needs no environment variable:
+  AC_SHARD_TRANSPORT=symm (default on NCCL groups with the CUDA back-end) | nccl
+        symm: the embed kernel writes into a symmetric-memory bank, every rank pulls the shards it needs with copy-engine copies
+        (symm_transport.SymmetricBank); nccl: all-gather / point-to-point collectives (automatic fallback, and always on gloo)
+  AC_SHARD_FLAGS=1 (default, symm only) | 0
+        1: ONE distance launch per step whose loader waits for per-bank-image arrival flags (ac_min_dist_sym_ready);
+        0: one launch per window of landed shards (AC_SHARD_MERGE=1 merges shards that will have landed anyway)
+  AC_SYMM_COLMIN=1 (default, symm only) | 0
+        1: column minima written into symmetric memory and collected with one ac_copy_blocks launch; 0: NCCL all_to_all
+  AC_SHARD_PIPELINE=1   (nccl transport, more than two ranks) shard-granular ring of pairwise exchanges, one launch per shard
+  AC_OVERLAP_MIN_WORLD  (nccl transport) smallest world size at which the local-shard launch overlaps the gather (default 2)"""
 from __future__ import annotations
 
 import functools

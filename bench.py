@@ -584,7 +584,9 @@ def main(argv=None):
         if mode == "percategory":
             par = "whole categories to ranks by LPT on n_c(n_c-1), no collective: %s" % (bins,) if world > 1 else "single GPU"
         elif world > 1:
-            par = "query-sharded x%d, operand all-gather + X gather (NCCL)" % world
+            transport = ("symmetric-memory pulls (copy engines) + one flag-driven distance launch" if os.environ.get("AC_SHARD_TRANSPORT", "symm") == "symm"
+                         else "NCCL collectives")
+            par = "query-sharded x%d, operand transport: %s, X gather (NCCL)" % (world, transport)
         else:
             par = "single GPU"
         line = {
