@@ -108,6 +108,7 @@ SIGNATURES = {
     "ac_reduce_weights": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "ac_alpha": (c_int, [c_void_p, c_int, c_int, POINTER(c_double), c_int, c_void_p, c_void_p, c_void_p]),
     "ac_weighted_embed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ac_weighted_embed_multi": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ac_weighted_embed_from_features_workspace_bytes": (c_size_t, [POINTER(AcLayer), c_int, c_int, c_int]),
     "ac_weighted_embed_from_features": (
         c_int,

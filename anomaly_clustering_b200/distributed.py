@@ -259,6 +259,13 @@ def gather_needed_rows(local, bounds, rows_per_item, need, group=None) -> torch.
     return buf
 
 
+def _weighted_embed_all_taus(compute, a32, Z3, T: int) -> torch.Tensor:
+    """[n_r, T, D]: one pass over Z for all taus when the compute back-end has the fused form (the CUDA library), else per tau."""
+    if hasattr(compute, "weighted_embed_multi"):
+        return compute.weighted_embed_multi(a32, Z3).transpose(0, 1).contiguous()
+    return torch.stack([compute.weighted_embed(a32[t], Z3) for t in range(T)], dim=1)
+
+
 def exchange_colmin(colmin: torch.Tensor, bounds: Sequence[Tuple[int, int]], P: int, group=None) -> torch.Tensor:
     """Symmetric mode: rank r holds colmin [n_r, N*P] = (its images as BANK image, every global query
     row); the owner of query rows [a*P, b*P) needs those columns from every rank.  All-to-all of the
@@ -313,6 +320,7 @@ def run_path_sharded(
             min_distance_weights = staticmethod(pipeline.min_distance_weights)
             alpha = staticmethod(ops.alpha)
             weighted_embed = staticmethod(ops.weighted_embed)
+            weighted_embed_multi = staticmethod(ops.weighted_embed_multi)
             pairwise_l2 = staticmethod(ops.pairwise_l2)
             min_dist_sym = staticmethod(ops.min_dist_sym)
             supports_bank_window = True
@@ -528,7 +536,7 @@ def run_path_sharded(
                              for t in range(len(taus))], dim=1)
     else:
         Z3 = q.Z.reshape(q.n_img, P, q.D)
-        X_loc = torch.stack([compute.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)  # [n_r, T, D]
+        X_loc = _weighted_embed_all_taus(compute, a32, Z3, len(taus))                               # [n_r, T, D]
     pipeline._mark("xgather_begin")
     X_all = all_gather_rows(X_loc, [b - a for a, b in bounds], group).permute(1, 0, 2).contiguous()  # [T, N, D]
     pipeline._mark("xgather_end")
@@ -569,6 +577,7 @@ def run_path_sharded_supervised(
             min_distance_weights = staticmethod(pipeline.min_distance_weights)
             alpha = staticmethod(ops.alpha)
             weighted_embed = staticmethod(ops.weighted_embed)
+            weighted_embed_multi = staticmethod(ops.weighted_embed_multi)
             pairwise_l2 = staticmethod(ops.pairwise_l2)
 
         compute = _Cuda
@@ -617,7 +626,7 @@ def run_path_sharded_supervised(
             w = wp if w is None else torch.minimum(w, wp)
     a64, a32 = compute.alpha(w, list(taus))
     Z3 = q.Z.reshape(q.n_img, P, q.D)
-    X_loc = torch.stack([compute.weighted_embed(a32[t], Z3) for t in range(len(taus))], dim=1)      # [n_r, T, D]
+    X_loc = _weighted_embed_all_taus(compute, a32, Z3, len(taus))                                   # [n_r, T, D]
     pipeline._mark("xgather_begin")
     X_all = all_gather_rows(X_loc, [b - a for a, b in qb], group).permute(1, 0, 2).contiguous()     # [T, N, D]
     pipeline._mark("xgather_end")

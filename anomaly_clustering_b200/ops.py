@@ -374,6 +374,19 @@ def weighted_embed(alpha32: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
     return X
 
 
+def weighted_embed_multi(alpha32: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
+    """X [T, N, D] for alpha [T, N, P] from ONE pass over Z [N, P, D] (ac_weighted_embed_multi): a tau sweep re-read Z per tau."""
+    lib = _lib.load()
+    _need_cuda(alpha32, Z)
+    N, P, D = Z.shape
+    T = alpha32.shape[0]
+    a = alpha32.reshape(T, N, P).contiguous().float()
+    assert Z.is_contiguous() and Z.dtype == torch.float32
+    X = torch.empty(T, N, D, dtype=torch.float32, device=Z.device)
+    check(lib.ac_weighted_embed_multi(_ptr(a), _ptr(Z), T, N, P, D, _ptr(X), _stream()), "ac_weighted_embed_multi")
+    return X
+
+
 def _layer_array(features):
     views = [feature_view(f) for f in features]
     _need_cuda(*views)

@@ -250,7 +250,7 @@ def alpha_X_dist(ps: PatchSet, w: Optional[torch.Tensor], taus: Sequence[float],
         a64, a32 = ops.alpha(w, taus)
     if ps.Z is not None:
         Z3 = ps.Z.reshape(N, P, D)
-        X = torch.stack([ops.weighted_embed(a32[t], Z3) for t in range(a32.shape[0])])
+        X = ops.weighted_embed_multi(a32, Z3)                    # [T, N, D], Z read once for all taus
     else:
         patchsize, stride, Dp, layernorm = embed_args
         X = torch.stack([ops.weighted_embed_from_features(features, a32[t], patchsize, stride, Dp, D, layernorm=layernorm)

@@ -236,6 +236,10 @@ int ac_alpha(const float* w, int N, int P, const double* taus_host, int T, doubl
 int ac_weighted_embed(const float* alpha, const float* Z, int N, int P, int D, float* X,
                       ac_stream_t stream);
 
+/* The same for T temperatures in ONE pass over Z (a tau sweep calls the bmm line once per tau, examples/main.py:294-296 inside the
+ * loop of :353): alpha [T, N, P], X [T, N, D]; bit-identical to T calls of ac_weighted_embed. */
+int ac_weighted_embed_multi(const float* alpha, const float* Z, int T, int N, int P, int D, float* X, ac_stream_t stream);
+
 /* X without Z: Z is a fixed linear map of the LayerNorm'd feature maps, so
  * X[i] = sum_p alpha[i,p] Z[i,p] = Pool(A_i) with A_i[c,ki,kj] = sum_p alpha[i,p] * LN_i[c, y_p+ki-1, x_p+kj-1]:
  * a 3x3 correlation of the alpha map with every channel, then the MeanMapper / Aggregator windows once per

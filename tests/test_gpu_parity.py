@@ -499,6 +499,21 @@ def test_alpha_edge_cases():
     assert (a64[1].cpu() - want).abs().max().item() <= 1e-12
 
 
+@pytest.mark.parametrize("T,N,P,D", [(1, 3, 50, 128), (3, 4, 96, 512), (6, 2, 200, 1024), (17, 3, 64, 256), (5, 2, 40, 130)])
+def test_weighted_embed_all_taus_in_one_pass(T, N, P, D):
+    """ac_weighted_embed_multi (X for every tau of a sweep from one pass over Z) is bit-identical to one ac_weighted_embed per
+    tau (examples/main.py:294-296 inside the tau loop), including tau groups of 8 / 4 / 2 / 1 and a D the vector kernel refuses."""
+    gen = torch.Generator(device="cuda").manual_seed(T * 100 + D)
+    Z = torch.randn(N, P, D, generator=gen, device="cuda")
+    a = torch.softmax(torch.randn(T, N, P, generator=gen, device="cuda") * 3, dim=2)
+    got = ops.weighted_embed_multi(a, Z)
+    want = torch.stack([ops.weighted_embed(a[t], Z) for t in range(T)])
+    torch.cuda.synchronize()
+    assert got.shape == (T, N, D) and torch.equal(got, want)
+    ref = torch.bmm(a.double().reshape(T * N, 1, P), Z.double().repeat(T, 1, 1)).reshape(T, N, D)
+    assert (got.double() - ref).abs().max().item() <= 1e-5
+
+
 def test_copy_blocks_strided_batched():
     """ac_copy_blocks (the sharded path's collection of column-minimum blocks): several strided 2-D blocks in one launch,
     16-byte and 4-byte aligned shapes, float and 64-bit elements -- bit-exact against torch's copy."""
