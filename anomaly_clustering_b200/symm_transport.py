@@ -12,9 +12,16 @@ allocated as torch symmetric memory (CUDA VMM allocations mapped into every rank
     they run on the copy engines at NVLink speed, cost no SM while the persistent GEMM is running, and each shard has
     its own event, so the GEMM window of shard k starts as soon as shard k has landed (ring order rank+1, rank+2, ...).
 
-Two buffer sets alternate between steps, so ONE barrier per step is enough: a rank reaches the barrier of step t+1 only
-after its stream has consumed every shard it pulled in step t, hence after that barrier the set of step t may be
-overwritten (that happens in step t+2)."""
+Two buffer sets alternate between steps, so ONE barrier per buffer kind and step is enough: a rank reaches the barrier of step
+t+1 only after its stream has consumed every shard it pulled in step t, hence after that barrier the set of step t may be
+overwritten (that happens in step t+2).
+
+The same object carries the two later stages of the step:
+  * arrival flags -- publish_and_pull(ready=...) sets one int32 per bank image on the side stream right after the shard that holds
+    it has landed; the distance kernel (ac_min_dist_sym_ready) is launched ONCE over the whole bank and waits per bank image;
+  * the column-minimum exchange -- colmin_buffer() hands the distance kernel a symmetric buffer for its column minima,
+    exchange_colmin() is one more barrier plus one batched strided read (ac_copy_blocks) of this rank's columns out of every
+    peer's buffer, instead of an NCCL all_to_all."""
 from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
