@@ -75,6 +75,7 @@ struct __align__(64) TcParams {
   // sharded runs: bank_ready[j] != 0 once bank image j (operand rows + norms) has landed in this GPU's memory; the producer
   // waits for it before the first load of a unit.  null = the whole bank is resident.
   const int* bank_ready;
+  int img_rot;                   // all-pairs form: the raster starts at this bank image (the first one that is resident in a sharded run)
   int* rowarg;                   // [nb_img, Mq] row inside bank image j that is nearest to query row r
   unsigned long long* colkey;    // sym: [nq_img, nb_img*P] (fp32 bits of d2 << 32) | row inside the query image, atomicMin target
 };
@@ -363,7 +364,8 @@ __device__ __forceinline__ bool decode_unit(const TcParams& p, long long u, int&
   const int gm_cur = min(p.GM, p.n_mblocks - mg * p.GM);
   const int k = (int)(rem / gm_cur);
   mb = mg * p.GM + (int)(rem - (long long)k * gm_cur);
-  img = k;
+  img = k + p.img_rot;
+  if (img >= p.nb_img) img -= p.nb_img;
   return true;
 }
 
@@ -904,7 +906,7 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
                       const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int* err_flag, cudaStream_t st,
                       int sym = 0, int q_img0 = 0, unsigned int* colmin = nullptr, void* unit_ws = nullptr, size_t unit_ws_bytes = 0,
                       int win_begin = 0, int win_count = -1, int* rowarg = nullptr, unsigned long long* colkey = nullptr,
-                      const int* groups = nullptr, const int* bank_ready = nullptr) {
+                      const int* groups = nullptr, const int* bank_ready = nullptr, int img_rot = 0) {
   const bool bf16 = (precision == AC_PREC_BF16 || precision == AC_PREC_BF16X3);
   const bool x3 = (precision == AC_PREC_F16X3 || precision == AC_PREC_BF16X3);
   if (D % 8 != 0) return AC_ERR_UNSUPPORTED;  // TMA needs a 16-byte row pitch
@@ -928,7 +930,7 @@ int launch_mindist_tc(const void* Qhi, const void* Qlo, const float* Qn2, long l
   prm.dynamic = g_tc_dynamic;
   prm.counter = (unsigned long long*)((char*)err_flag + 128);   // inside the zeroed 256-byte workspace header
   prm.sym = sym; prm.q_img0 = q_img0; prm.colmin = colmin; prm.units = nullptr;
-  prm.rowarg = rowarg; prm.colkey = colkey; prm.groups = groups; prm.bank_ready = bank_ready;
+  prm.rowarg = rowarg; prm.colkey = colkey; prm.groups = groups; prm.bank_ready = bank_ready; prm.img_rot = sym ? 0 : img_rot;
   const bool arg = (rowarg != nullptr);
   if (arg && sym && !colkey) return AC_ERR_INVALID;
   prm.win_begin = win_begin; prm.win_count = (win_count < 0) ? nb_img : win_count;
@@ -1143,8 +1145,10 @@ extern "C" size_t ac_min_dist_workspace_bytes(int64_t Mq, int nb_img, int P, int
 
 static int min_dist_impl(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
                          const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int32_t* argmin, void* ws,
-                         size_t ws_bytes, ac_stream_t stream) {
+                         size_t ws_bytes, ac_stream_t stream, const int32_t* bank_ready = nullptr, int first_bank_image = 0) {
   if (!Qhi || !Bhi || !dmin || Mq < 0 || nb_img < 1 || P < 1 || D < 1) return AC_ERR_INVALID;
+  if (first_bank_image < 0 || first_bank_image >= nb_img) return AC_ERR_INVALID;
+  if (bank_ready && precision == AC_PREC_F32) return AC_ERR_UNSUPPORTED;   // arrival flags: tensor-core kernel only
   if (argmin && precision == AC_PREC_F32) return AC_ERR_UNSUPPORTED;   // the exact kernel needs no refinement
   if (precision < AC_PREC_F16 || precision > AC_PREC_F32) return AC_ERR_INVALID;
   int rc = check_device();
@@ -1158,7 +1162,14 @@ static int min_dist_impl(const void* Qhi, const void* Qlo, const float* Qn2, int
   fill_u32_kernel<<<1, 64, 0, st>>>((unsigned int*)ws, 64, 0u);   // watchdog flag (no copy-engine memset)
   AC_LAUNCH_CHECK();
   return launch_mindist_tc(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, dmin, (int*)ws, st, 0, 0, nullptr, nullptr, 0, 0,
-                           -1, argmin, nullptr);
+                           -1, argmin, nullptr, nullptr, bank_ready, first_bank_image);
+}
+
+extern "C" int ac_min_dist_ready(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
+                                 const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int32_t* argmin,
+                                 const int32_t* bank_ready, int first_bank_image, void* ws, size_t ws_bytes, ac_stream_t stream) {
+  return min_dist_impl(Qhi, Qlo, Qn2, Mq, Bhi, Blo, Bn2, nb_img, P, D, precision, dmin, argmin, ws, ws_bytes, stream, bank_ready,
+                       first_bank_image);
 }
 
 extern "C" int ac_min_dist(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,

@@ -580,7 +580,9 @@ def run_path_sharded_supervised(
             weighted_embed_multi = staticmethod(ops.weighted_embed_multi)
             pairwise_l2 = staticmethod(ops.pairwise_l2)
 
-        compute = _Cuda
+        compute = _CUDA_SUPERVISED = _Cuda
+    else:
+        _CUDA_SUPERVISED = None
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if n_total < world or n_bank_total < world:
@@ -599,6 +601,46 @@ def run_path_sharded_supervised(
         Zb, hib, lob, n2b = bufs
         cut = lambda t: None if t is None else t[a * P : b * P]  # noqa: E731
         return pipeline.PatchSet(b - a, P, q.D, q.grid, Z=cut(Zb), hi=cut(hib), lo=cut(lob), n2=cut(n2b))
+
+    # Symmetric-memory transport for the bank (default on NCCL groups with the CUDA back-end, as in run_path_sharded): the bank
+    # shard is embedded straight into a symmetric buffer, every rank pulls the other shards with copy-engine copies, and ONE
+    # all-pairs launch walks the bank from the local shard on while they land (arrival flags, ac_min_dist_ready).
+    symm_bank = None
+    if (world > 1 and compute is _CUDA_SUPERVISED and precision != "f32" and dist.get_backend(group) == "nccl" and P >= 1
+            and os.environ.get("AC_SHARD_TRANSPORT", "symm") == "symm" and os.environ.get("AC_SHARD_FLAGS", "1") == "1"):
+        from .symm_transport import SymmetricBank
+
+        if SymmetricBank.disabled_reason is None:
+            operand, want_lo = pipeline._OPERAND_OF[precision]
+            try:
+                symm_bank = SymmetricBank.get(n_bank_total * P, target_dim, torch.float16 if operand == "f16" else torch.bfloat16,
+                                              want_lo, q.hi.device, group)
+            except Exception as e:  # noqa: BLE001 -- symmetric memory unavailable: say so once, use NCCL
+                SymmetricBank.disabled_reason = repr(e)
+                import warnings
+
+                warnings.warn("symmetric-memory transport unavailable (%r): the sharded path uses NCCL collectives" % (e,))
+    if symm_bank is not None:
+        lo_b, hi_b = bb[rank]
+        hi_s, lo_s, n2_s = symm_bank.local_slices(lo_b * P, hi_b * P)
+        hi_s.copy_(b_loc.hi)
+        if lo_s is not None:
+            lo_s.copy_(b_loc.lo)
+        n2_s.copy_(b_loc.n2)
+        pipeline._mark("gather_begin")
+        ready = torch.zeros(n_bank_total, dtype=torch.int32, device=q.hi.device)
+        ready[lo_b:hi_b] = 1
+        (hib, lob, n2b), steps = symm_bank.publish_and_pull(bb, P, [r for r in range(world) if r != rank], rank, world, ready=ready)
+        pipeline._mark("gather_end")
+        reqs = [r for _, rr in steps for r in rr]
+
+        def landed():
+            for r in reqs:
+                r.wait()
+
+        bank_all = pipeline.PatchSet(n_bank_total, P, q.D, q.grid, hi=hib, lo=lob, n2=n2b)
+        w = compute.min_distance_weights(q, bank_all, "supervised", precision, bank_ready=ready, bank_first=lo_b, bank_landed=landed)
+        return _supervised_tail(compute, pipeline, q, w, taus, qb, P, group)
 
     pipeline._mark("gather_begin")
     pending = []
@@ -624,6 +666,11 @@ def run_path_sharded_supervised(
         if b > a:
             wp = compute.min_distance_weights(q, piece(bufs, a, b), "supervised", precision)
             w = wp if w is None else torch.minimum(w, wp)
+    return _supervised_tail(compute, pipeline, q, w, taus, qb, P, group)
+
+
+def _supervised_tail(compute, pipeline, q, w, taus, qb, P, group):
+    """alpha, X of the local query rows, all-gather of the X rows, Dmat (stage 3 of run_path_sharded_supervised)."""
     a64, a32 = compute.alpha(w, list(taus))
     Z3 = q.Z.reshape(q.n_img, P, q.D)
     X_loc = _weighted_embed_all_taus(compute, a32, Z3, len(taus))                                   # [n_r, T, D]

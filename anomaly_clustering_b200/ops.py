@@ -197,8 +197,10 @@ def row_norms(A: torch.Tensor, A2: Optional[torch.Tensor] = None) -> torch.Tenso
     return out
 
 
-def min_dist(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dmin [nb_img, Mq]: per bank image, distance of each query row to its nearest bank row."""
+def min_dist(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, out: Optional[torch.Tensor] = None,
+             ready: Optional[torch.Tensor] = None, first_image: int = 0) -> torch.Tensor:
+    """dmin [nb_img, Mq]: per bank image, distance of each query row to its nearest bank row.
+    ready / first_image: arrival flags of a bank that is still landing and the bank image the walk starts at (ac_min_dist_ready)."""
     lib = _lib.load()
     _need_cuda(Qhi, Bhi)
     prec = _lib.PRECISIONS[precision]
@@ -208,8 +210,13 @@ def min_dist(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, 
     dmin = out if out is not None else torch.empty(nb_img, Mq, dtype=torch.float32, device=Qhi.device)
     ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
-    rc = lib.ac_min_dist(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec, _ptr(dmin),
-                         _ptr(ws), ws_bytes, _stream())
+    if ready is not None or first_image:
+        _ready_ok(ready, nb_img)
+        rc = lib.ac_min_dist_ready(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec, _ptr(dmin),
+                                   None, _ptr(ready), int(first_image), _ptr(ws), ws_bytes, _stream())
+    else:
+        rc = lib.ac_min_dist(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec, _ptr(dmin),
+                             _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_min_dist")
     return dmin
 
@@ -248,7 +255,8 @@ def min_dist_sym(Qhi, Qlo, Qn2, q_img0: int, Bhi, Blo, Bn2, nb_img: int, P: int,
     return rowmin, colmin
 
 
-def min_dist_arg(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str):
+def min_dist_arg(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: str, ready: Optional[torch.Tensor] = None,
+                 first_image: int = 0):
     """ac_min_dist_arg: (dmin [nb_img, Mq], argmin [nb_img, Mq] int32 = row inside bank image j nearest to query row r)."""
     lib = _lib.load()
     _need_cuda(Qhi, Bhi)
@@ -259,8 +267,9 @@ def min_dist_arg(Qhi, Qlo, Qn2, Bhi, Blo, Bn2, nb_img: int, P: int, precision: s
     arg = torch.empty(nb_img, Mq, dtype=torch.int32, device=Qhi.device)
     ws_bytes = lib.ac_min_dist_workspace_bytes(Mq, nb_img, P, D, prec)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=Qhi.device)
-    rc = lib.ac_min_dist_arg(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec, _ptr(dmin),
-                             _ptr(arg), _ptr(ws), ws_bytes, _stream())
+    _ready_ok(ready, nb_img)
+    rc = lib.ac_min_dist_ready(_ptr(Qhi), _ptr(Qlo), _ptr(Qn2), Mq, _ptr(Bhi), _ptr(Blo), _ptr(Bn2), nb_img, P, D, prec, _ptr(dmin),
+                               _ptr(arg), _ptr(ready), int(first_image), _ptr(ws), ws_bytes, _stream())
     check(rc, "ac_min_dist_arg")
     return dmin, arg
 

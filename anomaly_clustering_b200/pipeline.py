@@ -188,10 +188,16 @@ def min_distance_weights(
     q_self: Optional[torch.Tensor] = None,
     return_dmin: bool = False,
     groups: Optional[torch.Tensor] = None,
+    bank_ready: Optional[torch.Tensor] = None,
+    bank_first: int = 0,
+    bank_landed=None,
 ):
     """Stage 2: w [Nq, P].  mode 'unsupervised' = mean over bank images != self (utils.py:222-227),
     'supervised' = min over bank images (utils.py:230-237).  q_self[i] = bank index of query image i.
-    groups (ops.make_groups): the images are several categories back to back, each its own bank (symmetric form only)."""
+    groups (ops.make_groups): the images are several categories back to back, each its own bank (symmetric form only).
+    bank_ready / bank_first / bank_landed (sharded supervised runs): arrival flags of a bank whose remote shards are still being
+    pulled, the first resident bank image, and a callable that orders the current stream after all pulls (called before the
+    refine pass, which gathers from the whole bank)."""
     refined = precision in REFINED
     if (mode == "unsupervised" and SYMMETRIC and q is bank and precision != "f32" and q.P >= 32 and not return_dmin
             and q_self is None):
@@ -214,10 +220,14 @@ def min_distance_weights(
     if precision == "f32":
         dmin = ops.min_dist(q.Z, None, None, bank.Z, None, None, bank.n_img, bank.P, "f32")
     elif refined:
-        dmin, arg = ops.min_dist_arg(q.hi, q.lo, q.n2, bank.hi, bank.lo, bank.n2, bank.n_img, bank.P, precision)
+        dmin, arg = ops.min_dist_arg(q.hi, q.lo, q.n2, bank.hi, bank.lo, bank.n2, bank.n_img, bank.P, precision, ready=bank_ready,
+                                     first_image=bank_first)
     else:
-        dmin = ops.min_dist(q.hi, q.lo, q.n2, bank.hi, bank.lo, bank.n2, bank.n_img, bank.P, precision)
+        dmin = ops.min_dist(q.hi, q.lo, q.n2, bank.hi, bank.lo, bank.n2, bank.n_img, bank.P, precision, ready=bank_ready,
+                            first_image=bank_first)
     _mark("mindist_end")
+    if bank_landed is not None:
+        bank_landed()
     if refined:
         if mode == "unsupervised" and q_self is None:
             q_self = torch.arange(q.n_img, dtype=torch.int32, device=dmin.device)

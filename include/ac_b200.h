@@ -188,6 +188,13 @@ int ac_reduce_weights_sym(const float* rowmin_d2, const float* colmin_d2, int64_
 int ac_min_dist_arg(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
                     const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int32_t* argmin, void* ws,
                     size_t ws_bytes, ac_stream_t stream);
+
+/* ac_min_dist / ac_min_dist_arg (argmin may be NULL) for a bank that is still ARRIVING (sharded supervised runs; see
+ * ac_min_dist_sym_ready): bank_ready [nb_img] int32 arrival flags in device memory (NULL = resident), first_bank_image = where the
+ * walk over the bank images starts (the first resident one; the others are visited in increasing order, wrapping around). */
+int ac_min_dist_ready(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, const void* Bhi, const void* Blo,
+                      const float* Bn2, int nb_img, int P, int D, int precision, float* dmin, int32_t* argmin,
+                      const int32_t* bank_ready, int first_bank_image, void* ws, size_t ws_bytes, ac_stream_t stream);
 int ac_min_dist_sym_arg(const void* Qhi, const void* Qlo, const float* Qn2, int64_t Mq, int q_img0, const void* Bhi,
                         const void* Blo, const float* Bn2, int nb_img, int P, int D, int precision, int bank_begin,
                         int bank_count, int init_colkey, float* rowmin_d2, int32_t* rowarg, uint64_t* colkey, void* ws,

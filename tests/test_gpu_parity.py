@@ -343,6 +343,46 @@ def test_mindist_symmetric_waits_for_arriving_bank(arg):
         assert torch.equal(g, w_)
 
 
+@pytest.mark.parametrize("arg", [False, True])
+def test_mindist_all_pairs_waits_for_arriving_bank(arg):
+    """ac_min_dist_ready (sharded supervised runs): the walk over the bank starts at the first resident image, the other
+    shards' rows and norms are copied in by another stream after the kernel has started; same bits as with a resident bank."""
+    nb, P, D, nq = 8, 96, 256, 3
+    gen = torch.Generator().manual_seed(23)
+    Zb = (torch.randn(1, P, D, generator=gen) + 0.5 * torch.randn(nb, P, D, generator=gen)).cuda()
+    Zq = (torch.randn(1, P, D, generator=gen) + 0.5 * torch.randn(nq, P, D, generator=gen)).cuda()
+    bank, q = pipeline.patchset_from_Z(Zb, "f16"), pipeline.patchset_from_Z(Zq, "f16")
+    launch = ops.min_dist_arg if arg else ops.min_dist
+    want = launch(q.hi, None, q.n2, bank.hi, None, bank.n2, nb, P, "f16")
+    torch.cuda.synchronize()
+    first, n_local = 5, 2                                      # resident: images 5, 6; arrival order 7, 0, 1, 2, 3, 4
+    hi = torch.full_like(bank.hi, float("nan"))
+    n2 = torch.full_like(bank.n2, float("nan"))
+    ready = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    loc = slice(first * P, (first + n_local) * P)
+    hi[loc], n2[loc] = bank.hi[loc], bank.n2[loc]
+    ready[first:first + n_local] = 1
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for k in range(n_local, nb, 2):
+            torch.cuda._sleep(int(2.0e7))
+            for j in ((first + k) % nb, (first + k + 1) % nb):
+                sl = slice(j * P, (j + 1) * P)
+                hi[sl].copy_(bank.hi[sl], non_blocking=True)
+                n2[sl].copy_(bank.n2[sl], non_blocking=True)
+                ready[j:j + 1].fill_(1)
+    got = launch(q.hi, None, q.n2, hi, None, n2, nb, P, "f16", ready=ready, first_image=first)
+    torch.cuda.synchronize()
+    if arg:
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    else:
+        assert torch.equal(got, want)
+    # the rotated walk alone (resident bank) changes nothing either
+    rot = launch(q.hi, None, q.n2, bank.hi, None, bank.n2, nb, P, "f16", first_image=3)
+    assert torch.equal(rot[0] if arg else rot, want[0] if arg else want)
+
+
 def test_mindist_symmetric_sharded_slices():
     """Two query slices of one bank (what two ranks compute) + the column-block exchange reproduce the
     single-slice result."""
