@@ -3,7 +3,7 @@
 #  1. the driver's own scaling command (bench.py under torchrun, default workload);  2. scripts/r02_multi.py (checks against one
 #  GPU, every workload's bench line, timelines) in one process group.
 N=${1:-2}
-OUT=gpurun_out/r02_multi_v6
+OUT=gpurun_out/r02_multi_v7
 mkdir -p $OUT
 nvidia-smi --query-gpu=index,name,clocks.sm,power.draw --format=csv > $OUT/gpus_n$N.txt 2>&1
 ( time timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus $N --steps 30 --warmup 3 ) > $OUT/driver_style_bench_n$N.json 2> $OUT/driver_style_bench_n$N.err; echo "driver-style bench rc=$?"
