@@ -69,6 +69,35 @@ def test_shard_bounds_and_lpt():
     assert max(loads) / (sum(loads) / 4) < 1.25                           # imbalance bound quoted in SURVEY 8e
 
 
+def test_all_tau_weighted_embed_uses_the_fused_form_when_the_backend_has_it():
+    """distributed._weighted_embed_all_taus: [n_r, T, D] from one pass over Z when the compute back-end offers
+    weighted_embed_multi (the CUDA library), else one weighted_embed per tau -- same numbers either way."""
+    gen = torch.Generator().manual_seed(3)
+    T, n, P, D = 4, 3, 10, 8
+    a32 = torch.softmax(torch.randn(T, n, P, generator=gen), dim=2)
+    Z3 = torch.randn(n, P, D, generator=gen)
+    calls = []
+
+    class PerTau:
+        @staticmethod
+        def weighted_embed(a, Z):
+            calls.append("one")
+            return torch.bmm(a.reshape(n, 1, P), Z).reshape(n, D)
+
+    class Fused(PerTau):
+        @staticmethod
+        def weighted_embed_multi(a, Z):
+            calls.append("multi")
+            return torch.einsum("tnp,npd->tnd", a, Z)
+
+    x1 = distributed._weighted_embed_all_taus(PerTau, a32, Z3, T)
+    assert calls == ["one"] * T and x1.shape == (n, T, D)
+    calls.clear()
+    x2 = distributed._weighted_embed_all_taus(Fused, a32, Z3, T)
+    assert calls == ["multi"] and x2.shape == (n, T, D) and x2.is_contiguous()
+    assert torch.allclose(x1, x2, atol=1e-6)
+
+
 class _OracleCompute:
     """Stand-in compute for the CPU test (oracle arithmetic on CPU tensors)."""
 
